@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the SSNT lattice forward-backward hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2]
+
+One "step" = one loss+grad pass of the hot path over one batch of synthetic log-probs.  The
+default workload is BASELINE.json configs[1] — B=32 U=128 T=800 fp32 — per GPU (weak scaling:
+every rank owns B=32 independent utterances; the only collective is the all-reduce of the
+scalar loss).  Prints ONE JSON line (rank 0).
+
+* value      lattice cells/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+* e2e        same metric through the C-ABI with HOST (pinned) buffers: H2D of the inputs and D2H
+             of log-likelihoods, loss and both gradient tensors inside the timed region.
+* roofline   fb kernel: algorithmic bytes (16 B/cell: read emit+shift, write two gradients)
+             / average launch duration, against the measured HBM copy bandwidth.
+* cpu_baseline  the CPU oracle's fp32 port (oracle/, the restatement standing in for the Rust
+             reference, which has no forward-backward and cannot be built here) on all host
+             cores, bounded sample.  --impl reference runs only that arm.
+
+L2 policy: the working set of one step (65 MB) fits the 126 MB L2, so the timed loop rotates
+through NSETS independent input/output/scratch sets (> 3x L2 in total); every step's inputs
+come from HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, T, U)
+    "cfg1": (1, 120, 32),
+    "cfg2": (32, 800, 128),
+    "cfg5s": (512, 2000, 256),   # a 1/8 slice of configs[4] (B=4096) per GPU
+}
+BYTES_PER_CELL = 16  # read log_emit+log_shift, write grad_emit+grad_shift (fp32)
+
+
+def load_product():
+    name = "ssnt_tts_rust_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = os.path.join(ROOT, "ssnt-tts-rust_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(pkg, "__init__.py"),
+                                                  submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ---- synthetic data: counter-based, keyed by the GLOBAL (b, t, u) index -------------------------
+def _mix64_np(x):
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def synthetic_numpy(b0, B, T, U, seed=1234):
+    """z ~ N(0,1) from a splitmix64 counter; log_emit = log sigmoid(z), log_shift = log sigmoid(-z)."""
+    with np.errstate(over="ignore"):
+        idx = (np.arange(b0 * T * U, (b0 + B) * T * U, dtype=np.uint64) * np.uint64(2)
+               + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15))
+        u1 = (_mix64_np(idx) >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+        u2 = (_mix64_np(idx + np.uint64(1)) >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+    z = np.sqrt(-2.0 * np.log(u1 + 1e-300)) * np.cos(2.0 * np.pi * u2)
+    le = -np.logaddexp(0.0, -z)
+    ls = -np.logaddexp(0.0, z)
+    return le.reshape(B, T, U).astype(np.float32), ls.reshape(B, T, U).astype(np.float32)
+
+
+def synthetic_torch(b0, B, T, U, device, seed=1234):
+    """Same distribution generated on the device (cheap hash of the global cell index)."""
+    import torch
+    n = B * T * U
+    idx = torch.arange(b0 * T * U, b0 * T * U + n, device=device, dtype=torch.int64)
+
+    def mix(x):
+        x = (x ^ (x >> 30)) * -4658895280553007687      # 0xBF58476D1CE4E5B9 as int64
+        x = (x ^ (x >> 27)) * -7723592293110705685      # 0x94D049BB133111EB as int64
+        return x ^ (x >> 31)
+
+    k = idx * 2 + seed * -7046029254386353131           # 0x9E3779B97F4A7C15 as int64
+    u1 = ((mix(k) >> 11) & ((1 << 53) - 1)).double() / float(1 << 53)
+    u2 = ((mix(k + 1) >> 11) & ((1 << 53) - 1)).double() / float(1 << 53)
+    z = (torch.sqrt(-2.0 * torch.log(u1 + 1e-300)) * torch.cos(2.0 * torch.pi * u2)).float()
+    le = torch.nn.functional.logsigmoid(z).reshape(B, T, U).contiguous()
+    ls = torch.nn.functional.logsigmoid(-z).reshape(B, T, U).contiguous()
+    return le, ls
+
+
+# ---- clocks -------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._gpu = gpu_index
+        self._th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self._gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU arm ----------------------------------------------------------------------------------------------
+def cpu_arm(B, T, U, budget_s=12.0, min_reps=2, max_reps=200):
+    """Times the oracle's fp32 port (multi-threaded over the batch like rayon) on one batch of
+    the workload, repeated until ~budget_s of wall time.  Returns (cells/s, cores, reps, s/step)."""
+    import oracle
+    oracle.build()
+    cores = oracle.get_threads()
+    le, ls = synthetic_numpy(0, B, T, U)
+    oracle.forward_backward(le[:1], ls[:1], precision="f32")  # touch
+    reps, t0 = 0, time.perf_counter()
+    times = []
+    while reps < max_reps and (reps < min_reps or time.perf_counter() - t0 < budget_s):
+        s = time.perf_counter()
+        oracle.forward_backward(le, ls, precision="f32")
+        times.append(time.perf_counter() - s)
+        reps += 1
+    per = float(np.median(times))
+    return B * T * U / per, cores, reps, per
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, T, U = WORKLOADS[args.workload]
+    import oracle
+    oracle.build()
+    cores = oracle.get_threads()
+    le, ls = synthetic_numpy(0, B, T, U)
+    for _ in range(max(args.warmup, 1)):
+        oracle.forward_backward(le, ls, precision="f32")
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.forward_backward(le, ls, precision="f32")
+    dt = time.perf_counter() - t0
+    cells = B * T * U
+    val = cells * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "ssnt_fwd_bwd_lattice_cells_per_sec", "value": val, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: SSNT loss+grad B={B} U={U} T={T} fp32 on host cores",
+                   "note": "reference crate has no forward-backward and cannot be built here (no cargo); "
+                           "this arm is the oracle's fp32 C++ port of the authored spec, batch-parallel "
+                           "over all host cores like rayon"},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} passes over one B={B} batch"},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    P = load_product()
+    P.lib()
+    B, T, U = WORKLOADS[args.workload]
+    cells = B * T * U
+    set_bytes = cells * 4 * 4 + P.forward_backward_workspace_bytes(B, T, U)
+    nsets = max(2, min(16, int(np.ceil(3.2 * 126e6 / set_bytes))))
+    if set_bytes * nsets > 60e9:
+        nsets = max(1, int(60e9 // set_bytes))
+    b_global0 = rank * B
+    sets = []
+    for s in range(nsets):
+        le, ls = synthetic_torch(b_global0 + s * world * B, B, T, U, dev)
+        ws = torch.empty(P.forward_backward_workspace_bytes(B, T, U), dtype=torch.uint8, device=dev)
+        out = (torch.empty(B, device=dev), torch.empty(1, device=dev),
+               torch.empty(B, T, U, device=dev), torch.empty(B, T, U, device=dev))
+        sets.append((le, ls, ws, out))
+    torch.cuda.synchronize()
+
+    def step(i):
+        le, ls, ws, out = sets[i % nsets]
+        ll, loss, ge, gs = P.forward_backward(le, ls, workspace=ws, out=out)
+        if world > 1:
+            dist.all_reduce(loss)  # the path's only collective: 4 bytes
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for i in range(args.steps):
+            loss = step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        # keep sampling a little under load if the run was very short
+        if args.steps * 1e-4 < 0.3:
+            t_end = time.perf_counter() + 0.4
+            i = 0
+            while time.perf_counter() < t_end:
+                step(i)
+                i += 1
+            torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    final_loss = float(loss.item())
+
+    # kernel-only timing for the roofline (no collective, same rotation)
+    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ksteps = max(args.steps, 10)
+    kev0.record()
+    for i in range(ksteps):
+        le, ls, ws, out = sets[i % nsets]
+        P.forward_backward(le, ls, workspace=ws, out=out)
+    kev1.record()
+    torch.cuda.synchronize()
+    k_ms = kev0.elapsed_time(kev1) / ksteps
+    kernel_kind = P.fb_kernel_used()
+
+    # ---- e2e through the C-ABI with HOST (pinned) buffers --------------------------------------
+    hsets = []
+    for s in range(2):
+        le, ls, _, _ = sets[s % nsets]
+        h = dict(le=le.cpu().pin_memory(), ls=ls.cpu().pin_memory(),
+                 ll=torch.empty(B).pin_memory(), loss=torch.empty(1).pin_memory(),
+                 ge=torch.empty(B, T, U).pin_memory(), gs=torch.empty(B, T, U).pin_memory())
+        hsets.append(h)
+
+    def e2e_step(i):
+        h = hsets[i % 2]
+        P.forward_backward(h["le"].numpy(), h["ls"].numpy(),
+                           out=(h["ll"].numpy(), h["loss"].numpy(), h["ge"].numpy(), h["gs"].numpy()))
+        if world > 1:
+            l = h["loss"].to(dev)
+            dist.all_reduce(l)
+            return float(l.item())
+        return float(h["loss"][0])
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_loss = e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    h2d = 2 * cells * 4
+    d2h = 2 * cells * 4 + B * 4 + 4
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = BYTES_PER_CELL * cells / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": "ssnt_fwd_bwd_lattice_cells_per_sec",
+        "value": world * cells * args.steps / (ms * 1e-3),
+        "unit": "cells/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: batched SSNT loss+grad fp32 B={B} U={U} T={T} per GPU "
+                        f"(BASELINE configs[1] when cfg2), full lengths",
+            "global_batch": world * B, "parallelism": f"batch-sharded dp{world}, all-reduce of the scalar loss only",
+            "l2_policy": f"rotating {nsets} independent input/output/scratch sets "
+                         f"({nsets * set_bytes / 1e6:.0f} MB > 3x 126 MB L2); inputs come from HBM every step",
+            "fb_kernel": {1: "fb_warp_kernel (cluster of 2 warps, TMA ring)", 0: "fb_generic_kernel"}.get(kernel_kind),
+            "loss_check": final_loss,
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells},
+        "e2e": {"value": world * cells * e2e_steps / e2e_s, "unit": "cells/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "loss_check": e2e_loss},
+        "gpu_launches": args.steps,  # one fb kernel launch per step (the all-reduce is NCCL's)
+        "clocks": clk.summary(),
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "fb_traffic_bytes.json")
+    if os.path.exists(traffic_file):
+        try:
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get(args.workload)
+        except Exception:
+            pass
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, reps, per = cpu_arm(B, T, U)
+        line["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
+                                "sample": f"{reps} passes over one B={B} U={U} T={T} batch, "
+                                          f"{per * 1e3:.1f} ms each (oracle fp32 port, batch-parallel)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

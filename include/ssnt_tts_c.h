@@ -1,0 +1,151 @@
+/*
+ * ssnt_tts_c.h — C-ABI of the B200 (sm_100a) backend for the ssnt-tts-rust hot path.
+ *
+ * Drop-in boundary: the seven functions of the first block are exactly the `#[no_mangle] pub
+ * extern fn` symbols of the reference's `ssnt_tts_c` crate (ssnt_tts_c/src/lib.rs), with the
+ * argument order, int32 sizes, 1-byte bool and caller-owned dense row-major buffers the
+ * reference's TensorFlow ops bind (ssnt-tts-tensorflow/src/[name]_op.cc, cited per function).
+ * libssnt_tts_c.so replaces the reference's libssnt_tts_c.a at link time.
+ *
+ * Memory spaces.  Every pointer argument of one call must live in the same memory space:
+ *   - device pointers (cudaMalloc / framework GPU tensors): the call only enqueues kernels on
+ *     the stream set with ssnt_tts_set_stream() and returns; nothing is copied.
+ *   - host pointers (what the reference's DEVICE_CPU ops pass today): inputs are staged to the
+ *     GPU, the same kernels run, outputs are copied back and the call returns when the host
+ *     buffers are complete.  There is no CPU implementation behind this header.
+ * The space is detected from the first pointer argument (cudaPointerGetAttributes) unless
+ * ssnt_tts_set_memory_space() pins it.
+ *
+ * Errors.  The reference panics (process abort) on null pointers and on the data-dependent
+ * asserts src/v2.rs:292 and src/v2_util.rs:58.  Null pointers abort here as well.  The
+ * data-dependent asserts are detected on the device: host-pointer calls abort before
+ * returning (same observable behaviour), device-pointer calls raise a flag that
+ * ssnt_tts_synchronize() turns into the abort (ssnt_tts_last_error() reads it without
+ * aborting).
+ */
+#ifndef SSNT_TTS_C_H_
+#define SSNT_TTS_C_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Block 1 — the reference's own symbols (signatures kept verbatim).
+ * ---------------------------------------------------------------------------------------- */
+
+/* v1 Emit/Shift beam step, single batch.  Replaces ssnt_tts_c/src/lib.rs:10-83 (→
+ * src/lib.rs:121-230); bound by ssnt_tts_beam_search_decode_op.cc:5-8.
+ * h[W,2] log_prob_history[W] is_finished[W] t[W] u[W] → all outputs [W]. */
+void ssnt_tts_beam_search_decode(const float *h, const float *log_prob_history,
+                                 const bool *is_finished, const int *t, const int *u, int max_t,
+                                 int beam_width, int *prediction, float *log_probs, int *next_t,
+                                 int *next_u, bool *next_is_finished, int *beam_branch);
+
+/* Best-beam back-trace.  Replaces ssnt_tts_c/src/lib.rs:86-116 (→ src/util.rs:20-33); bound by
+ * ssnt_extract_best_beam_branch_op.cc:6-8.  beam_branch,t_history [max_u,W] → [max_u] each. */
+void ssnt_extract_best_beam_branch(int best_final_branch, const int *beam_branch,
+                                   const int *t_history, int beam_width, int max_u,
+                                   int *best_beam_branch, int *best_t_history);
+
+/* v2 duration-class beam step.  Replaces ssnt_tts_c/src/lib.rs:118-218 (→ src/v2.rs:221-339);
+ * bound by ssnt_tts_v2_beam_search_decode_op.cc:5-26.  h[B,W,D], duration_table[D],
+ * input_length/output_length[B], everything else [B,W]. */
+void ssnt_tts_v2_beam_search_decode(const float *h, const float *log_prob_history,
+                                    const bool *is_finished, const int *total_duration,
+                                    const int *duration_table, const int *t, const int *u,
+                                    const int *input_length, const int *output_length,
+                                    int batch_size, int beam_width, int duration_class_size,
+                                    int zero_duration_id, bool allow_skip, bool test_mode,
+                                    int *prediction, float *log_probs, int *next_t, int *next_u,
+                                    bool *next_is_finished, int *next_total_duration,
+                                    int *beam_branch);
+
+/* Back-trace of every final beam.  Replaces ssnt_tts_c/src/lib.rs:220-241 (→
+ * src/v2_util.rs:6-36); bound by ssnt_order_beam_branch_op.cc:6-11.
+ * final_branch[B,W], beam_branch[B,T,W] → ordered_beam_branch[B,W,T]. */
+void ssnt_order_beam_branch(const int *final_branch, const int *beam_branch, int batch_size,
+                            int beam_width, int max_t, int *ordered_beam_branch);
+
+/* Duration → source-index upsampling.  Replaces ssnt_tts_c/src/lib.rs:244-265 (→
+ * src/v2_util.rs:39-66); bound by upsample_source_indexes_op.cc:6-12.  duration[B,W,T],
+ * output_length[B,W] → upsampled_source_indexes[B,W,max_u]; only the first output_length
+ * slots of each row are written (the caller pre-fills the rest, op.cc:75). */
+void ssnt_upsample_source_indexes(const int *duration, const int *output_length, int batch_size,
+                                  int beam_width, int max_t, int max_u,
+                                  int *upsampled_source_indexes);
+
+/* Tone-latent beam step.  Replaces ssnt_tts_c/src/lib.rs:267-343 (→
+ * src/tone_latent.rs:144-234); bound by tone_latent_beam_search_decode_op.cc:5-20. */
+void tone_latent_beam_search_decode(const float *h, const float *log_prob_history,
+                                    const bool *is_finished, const int *t, const int *u,
+                                    const int *input_length, int batch_size, int beam_width,
+                                    int tone_class_size, int empty_tone_id, int *prediction,
+                                    float *log_probs, int *next_t, int *next_u,
+                                    bool *next_is_finished, int *beam_branch);
+
+/* Batched Levenshtein distance, int32, bit-exact.  Replaces ssnt_tts_c/src/lib.rs:346-381 (→
+ * src/edit_distance.rs:6-60); bound by ssnt_tts_edit_distance.cc:6-9.
+ * a,b[B,max_length], a_lengths,b_lengths[B] → distance[B]. */
+void tone_latent_levenshtein_edit_distance(const int *a, const int *b, const int *a_lengths,
+                                           const int *b_lengths, int batch_size, int max_length,
+                                           int *distance);
+
+/* ------------------------------------------------------------------------------------------
+ * Block 2 — lattice forward-backward (no counterpart in the reference, which has no loss /
+ * gradient code; specification: DESIGN.md §2, SURVEY.md §8 a-FB / a-TL).  Same style: void,
+ * int32 sizes, caller-owned buffers.
+ *
+ * T = output frames (serial axis), U = input tokens; tensors are [B, max_t, max_u] row-major
+ * (U fastest).  t_len/u_len may be NULL (= full lengths).  Outputs:
+ *   log_likelihood[B]   natural-log likelihood per utterance (-inf if no path exists)
+ *   loss[1]             -sum_b log_likelihood[b]  (may be NULL)
+ *   grad_emit/shift     d log_likelihood / d log-prob = posterior transition occupancy;
+ *                       every element of the [B,max_t,max_u] tensors is written (padded,
+ *                       unreachable and infeasible cells get exactly 0).
+ * workspace: device memory of at least ssnt_tts_forward_backward_workspace_bytes(); NULL lets
+ * the library use an internal grow-only buffer (per host thread).
+ * ---------------------------------------------------------------------------------------- */
+size_t ssnt_tts_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u);
+void ssnt_tts_forward_backward(const float *log_emit, const float *log_shift, const int *t_len,
+                               const int *u_len, int batch_size, int max_t, int max_u,
+                               float *log_likelihood, float *loss, float *grad_emit,
+                               float *grad_shift, void *workspace, size_t workspace_bytes);
+
+/* Tone-latent marginalised lattice: log_emit/log_shift [B,max_t,max_u,K], log_tone [B,max_u,K]
+ * (log-prior of each token's tone class; cf. tone_class_size of src/tone_latent.rs:79-95). */
+size_t tone_latent_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u,
+                                                    int tone_class_size);
+void tone_latent_forward_backward(const float *log_emit, const float *log_shift,
+                                  const float *log_tone, const int *t_len, const int *u_len,
+                                  int batch_size, int max_t, int max_u, int tone_class_size,
+                                  float *log_likelihood, float *loss, float *grad_emit,
+                                  float *grad_shift, float *grad_tone, void *workspace,
+                                  size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Block 3 — runtime side channel (the reference ABI has no stream / device notion).
+ * ---------------------------------------------------------------------------------------- */
+/* cudaStream_t used by subsequent calls of the calling host thread (NULL = legacy stream). */
+void ssnt_tts_set_stream(void *cuda_stream);
+void *ssnt_tts_get_stream(void);
+/* 0 = auto-detect per call (default), 1 = treat pointers as host, 2 = as device. */
+void ssnt_tts_set_memory_space(int space);
+/* Waits for the current stream and aborts if a device-side assert fired (see "Errors"). */
+void ssnt_tts_synchronize(void);
+/* Waits for the current stream, returns and clears the error bits without aborting:
+ * 1 = v2 empty beam (src/v2.rs:292), 2 = upsample length mismatch (src/v2_util.rs:58),
+ * 4 = tone-latent empty beam, 8 = back-trace index out of range. */
+unsigned ssnt_tts_last_error(void);
+/* Forward-backward kernel selection for tests/benchmarks: -1 auto, 0 generic, 1 warp/TMA. */
+void ssnt_tts_set_fb_kernel(int kind);
+int ssnt_tts_get_fb_kernel_used(void);
+const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSNT_TTS_C_H_ */

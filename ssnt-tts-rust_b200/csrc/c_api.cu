@@ -1,0 +1,369 @@
+// extern "C" surface (include/ssnt_tts_c.h).  Mirrors ssnt_tts_c/src/lib.rs: every entry point
+// null-checks its pointers (assert!(!p.is_null()) there → abort here), derives the array lengths
+// from the scalar arguments exactly as the `from_raw_parts` calls do, and forwards to the compute
+// layer.  The one addition is the memory-space dispatch: device pointers are passed straight to
+// the kernels (asynchronous on the caller's stream); host pointers — what the reference's
+// DEVICE_CPU TensorFlow ops hand over — are staged to the GPU, the same kernels run, results are
+// copied back and the call returns once the host buffers are complete.  There is no CPU compute
+// path in this library.
+#include <vector>
+
+#include "../../include/ssnt_tts_c.h"
+#include "ssnt_common.cuh"
+
+namespace ssnt {
+// compute layer (device pointers), defined in the kernel translation units
+void v1_beam_search_decode(const float*, const float*, const bool*, const int*, const int*, int, int, int,
+                           int*, float*, int*, int*, bool*, int*, cudaStream_t);
+void v2_beam_search_decode(const float*, const float*, const bool*, const int*, const int*, const int*,
+                           const int*, const int*, const int*, int, int, int, int, bool, bool, int*,
+                           float*, int*, int*, bool*, int*, int*, cudaStream_t);
+void tone_beam_search_decode(const float*, const float*, const bool*, const int*, const int*, const int*,
+                             int, int, int, int, int*, float*, int*, int*, bool*, int*, cudaStream_t);
+void extract_best_beam_branch(int, const int*, const int*, int, int, int*, int*, cudaStream_t);
+void order_beam_branch(const int*, const int*, int, int, int, int*, cudaStream_t);
+void upsample_source_indexes(const int*, const int*, int, int, int, int, int*, cudaStream_t);
+void levenshtein_edit_distance(const int*, const int*, const int*, const int*, int, int, int*, cudaStream_t);
+
+namespace {
+
+#define NOT_NULL(p) SSNT_ASSERT((p) != nullptr, "assertion failed: !" #p ".is_null()")
+
+inline size_t n3(int a, int b, int c) { return (size_t)(a > 0 ? a : 0) * (b > 0 ? b : 0) * (c > 0 ? c : 0); }
+inline size_t n2(int a, int b) { return (size_t)(a > 0 ? a : 0) * (b > 0 ? b : 0); }
+
+// Host-pointer flavour: per-call staging through the thread's grow-only device scratch.
+class HostCall {
+public:
+    HostCall() : stream_(current_stream()) {}
+    template <typename T>
+    const T* in(const T* host, size_t n) {
+        T* d = (T*)device_scratch(slot_++, n * sizeof(T) + 16);
+        if (n) SSNT_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        return d;
+    }
+    // preload = the callee leaves some slots untouched, so the caller's pre-fill must survive
+    template <typename T>
+    T* out(T* host, size_t n, bool preload = false) {
+        T* d = (T*)device_scratch(slot_++, n * sizeof(T) + 16);
+        if (preload && n) SSNT_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, stream_));
+        outs_.push_back({d, host, n * sizeof(T)});
+        return d;
+    }
+    cudaStream_t stream() const { return stream_; }
+    // Copies results back; aborts (like the reference's panic) if a device-side assert fired, in
+    // which case the host outputs are left untouched.
+    void finish() {
+        SSNT_CUDA(cudaStreamSynchronize(stream_));
+        check_error_flag_or_panic();
+        for (auto& o : outs_)
+            if (o.bytes) SSNT_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream_));
+        SSNT_CUDA(cudaStreamSynchronize(stream_));
+    }
+
+private:
+    struct Out { void* dev; void* host; size_t bytes; };
+    cudaStream_t stream_;
+    int slot_ = 4;  // slots 0..3 are workspaces
+    std::vector<Out> outs_;
+};
+
+// Streams used to overlap H2D / kernel / D2H of batch chunks in the host-pointer lattice call.
+struct AuxStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    void init() {
+        if (s[0]) return;
+        for (int i = 0; i < 2; ++i) {
+            SSNT_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+            SSNT_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        SSNT_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    }
+};
+thread_local AuxStreams tls_aux;
+
+}  // namespace
+}  // namespace ssnt
+
+using namespace ssnt;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// ssnt_tts_c/src/lib.rs:10-83 — "Restricted to single batch."
+void ssnt_tts_beam_search_decode(const float* h, const float* log_prob_history, const bool* is_finished,
+                                 const int* t, const int* u, int max_t, int beam_width, int* prediction,
+                                 float* log_probs, int* next_t, int* next_u, bool* next_is_finished,
+                                 int* beam_branch) {
+    NOT_NULL(h); NOT_NULL(log_prob_history); NOT_NULL(is_finished); NOT_NULL(t); NOT_NULL(u);
+    NOT_NULL(prediction); NOT_NULL(log_probs); NOT_NULL(next_t); NOT_NULL(next_u);
+    NOT_NULL(next_is_finished); NOT_NULL(beam_branch);
+    const int batch_size = 1;
+    const size_t W = n2(batch_size, beam_width);
+    if (is_device_pointer(h)) {
+        v1_beam_search_decode(h, log_prob_history, is_finished, t, u, batch_size, max_t, beam_width,
+                              prediction, log_probs, next_t, next_u, next_is_finished, beam_branch,
+                              current_stream());
+        return;
+    }
+    HostCall c;
+    auto dh = c.in(h, W * 2); auto dl = c.in(log_prob_history, W); auto df = c.in(is_finished, W);
+    auto dt = c.in(t, W); auto du = c.in(u, W);
+    auto op = c.out(prediction, W); auto ol = c.out(log_probs, W); auto ot = c.out(next_t, W);
+    auto ou = c.out(next_u, W); auto of = c.out(next_is_finished, W); auto ob = c.out(beam_branch, W);
+    v1_beam_search_decode(dh, dl, df, dt, du, batch_size, max_t, beam_width, op, ol, ot, ou, of, ob, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:86-116
+void ssnt_extract_best_beam_branch(int best_final_branch, const int* beam_branch, const int* t_history,
+                                   int beam_width, int max_u, int* best_beam_branch, int* best_t_history) {
+    NOT_NULL(beam_branch); NOT_NULL(t_history); NOT_NULL(best_beam_branch); NOT_NULL(best_t_history);
+    const size_t n = n2(max_u, beam_width), m = (size_t)(max_u > 0 ? max_u : 0);
+    if (is_device_pointer(beam_branch)) {
+        extract_best_beam_branch(best_final_branch, beam_branch, t_history, beam_width, max_u,
+                                 best_beam_branch, best_t_history, current_stream());
+        return;
+    }
+    HostCall c;
+    auto db = c.in(beam_branch, n); auto dt = c.in(t_history, n);
+    auto ob = c.out(best_beam_branch, m); auto ot = c.out(best_t_history, m);
+    extract_best_beam_branch(best_final_branch, db, dt, beam_width, max_u, ob, ot, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:118-218
+void ssnt_tts_v2_beam_search_decode(const float* h, const float* log_prob_history, const bool* is_finished,
+                                    const int* total_duration, const int* duration_table, const int* t,
+                                    const int* u, const int* input_length, const int* output_length,
+                                    int batch_size, int beam_width, int duration_class_size,
+                                    int zero_duration_id, bool allow_skip, bool test_mode, int* prediction,
+                                    float* log_probs, int* next_t, int* next_u, bool* next_is_finished,
+                                    int* next_total_duration, int* beam_branch) {
+    NOT_NULL(h); NOT_NULL(log_prob_history); NOT_NULL(is_finished); NOT_NULL(total_duration);
+    NOT_NULL(duration_table); NOT_NULL(t); NOT_NULL(u); NOT_NULL(input_length); NOT_NULL(output_length);
+    NOT_NULL(prediction); NOT_NULL(log_probs); NOT_NULL(next_t); NOT_NULL(next_u);
+    NOT_NULL(next_is_finished); NOT_NULL(next_total_duration); NOT_NULL(beam_branch);
+    const size_t BW = n2(batch_size, beam_width), B = (size_t)(batch_size > 0 ? batch_size : 0);
+    if (is_device_pointer(h)) {
+        v2_beam_search_decode(h, log_prob_history, is_finished, total_duration, duration_table, t, u,
+                              input_length, output_length, batch_size, beam_width, duration_class_size,
+                              zero_duration_id, allow_skip, test_mode, prediction, log_probs, next_t, next_u,
+                              next_is_finished, next_total_duration, beam_branch, current_stream());
+        return;
+    }
+    HostCall c;
+    auto dh = c.in(h, n3(batch_size, beam_width, duration_class_size));
+    auto dl = c.in(log_prob_history, BW); auto df = c.in(is_finished, BW);
+    auto dtd = c.in(total_duration, BW);
+    auto dtab = c.in(duration_table, (size_t)(duration_class_size > 0 ? duration_class_size : 0));
+    auto dt = c.in(t, BW); auto du = c.in(u, BW);
+    auto dil = c.in(input_length, B); auto dol = c.in(output_length, B);
+    auto op = c.out(prediction, BW); auto ol = c.out(log_probs, BW); auto ot = c.out(next_t, BW);
+    auto ou = c.out(next_u, BW); auto of = c.out(next_is_finished, BW);
+    auto otd = c.out(next_total_duration, BW); auto ob = c.out(beam_branch, BW);
+    v2_beam_search_decode(dh, dl, df, dtd, dtab, dt, du, dil, dol, batch_size, beam_width,
+                          duration_class_size, zero_duration_id, allow_skip, test_mode, op, ol, ot, ou, of,
+                          otd, ob, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:220-241
+void ssnt_order_beam_branch(const int* final_branch, const int* beam_branch, int batch_size, int beam_width,
+                            int max_t, int* ordered_beam_branch) {
+    NOT_NULL(final_branch); NOT_NULL(beam_branch); NOT_NULL(ordered_beam_branch);
+    if (is_device_pointer(final_branch)) {
+        order_beam_branch(final_branch, beam_branch, batch_size, beam_width, max_t, ordered_beam_branch,
+                          current_stream());
+        return;
+    }
+    HostCall c;
+    auto df = c.in(final_branch, n2(batch_size, beam_width));
+    auto db = c.in(beam_branch, n3(batch_size, max_t, beam_width));
+    auto oo = c.out(ordered_beam_branch, n3(batch_size, beam_width, max_t));
+    order_beam_branch(df, db, batch_size, beam_width, max_t, oo, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:244-265
+void ssnt_upsample_source_indexes(const int* duration, const int* output_length, int batch_size,
+                                  int beam_width, int max_t, int max_u, int* upsampled_source_indexes) {
+    NOT_NULL(duration); NOT_NULL(output_length); NOT_NULL(upsampled_source_indexes);
+    if (is_device_pointer(duration)) {
+        upsample_source_indexes(duration, output_length, batch_size, beam_width, max_t, max_u,
+                                upsampled_source_indexes, current_stream());
+        return;
+    }
+    HostCall c;
+    auto dd = c.in(duration, n3(batch_size, beam_width, max_t));
+    auto dl = c.in(output_length, n2(batch_size, beam_width));
+    auto oo = c.out(upsampled_source_indexes, n3(batch_size, beam_width, max_u), /*preload=*/true);
+    upsample_source_indexes(dd, dl, batch_size, beam_width, max_t, max_u, oo, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:267-343
+void tone_latent_beam_search_decode(const float* h, const float* log_prob_history, const bool* is_finished,
+                                    const int* t, const int* u, const int* input_length, int batch_size,
+                                    int beam_width, int tone_class_size, int empty_tone_id, int* prediction,
+                                    float* log_probs, int* next_t, int* next_u, bool* next_is_finished,
+                                    int* beam_branch) {
+    NOT_NULL(h); NOT_NULL(log_prob_history); NOT_NULL(is_finished); NOT_NULL(t); NOT_NULL(u);
+    NOT_NULL(input_length); NOT_NULL(prediction); NOT_NULL(log_probs); NOT_NULL(next_t); NOT_NULL(next_u);
+    NOT_NULL(next_is_finished); NOT_NULL(beam_branch);
+    const size_t BW = n2(batch_size, beam_width);
+    if (is_device_pointer(h)) {
+        tone_beam_search_decode(h, log_prob_history, is_finished, t, u, input_length, batch_size, beam_width,
+                                tone_class_size, empty_tone_id, prediction, log_probs, next_t, next_u,
+                                next_is_finished, beam_branch, current_stream());
+        return;
+    }
+    HostCall c;
+    auto dh = c.in(h, n3(batch_size, beam_width, tone_class_size));
+    auto dl = c.in(log_prob_history, BW); auto df = c.in(is_finished, BW);
+    auto dt = c.in(t, BW); auto du = c.in(u, BW);
+    auto dil = c.in(input_length, (size_t)(batch_size > 0 ? batch_size : 0));
+    auto op = c.out(prediction, BW); auto ol = c.out(log_probs, BW); auto ot = c.out(next_t, BW);
+    auto ou = c.out(next_u, BW); auto of = c.out(next_is_finished, BW); auto ob = c.out(beam_branch, BW);
+    tone_beam_search_decode(dh, dl, df, dt, du, dil, batch_size, beam_width, tone_class_size, empty_tone_id,
+                            op, ol, ot, ou, of, ob, c.stream());
+    c.finish();
+}
+
+// ssnt_tts_c/src/lib.rs:346-381
+void tone_latent_levenshtein_edit_distance(const int* a, const int* b, const int* a_lengths,
+                                           const int* b_lengths, int batch_size, int max_length,
+                                           int* distance) {
+    NOT_NULL(a); NOT_NULL(b); NOT_NULL(a_lengths); NOT_NULL(b_lengths); NOT_NULL(distance);
+    const size_t B = (size_t)(batch_size > 0 ? batch_size : 0);
+    if (is_device_pointer(a)) {
+        levenshtein_edit_distance(a, b, a_lengths, b_lengths, batch_size, max_length, distance, current_stream());
+        return;
+    }
+    HostCall c;
+    auto da = c.in(a, n2(batch_size, max_length)); auto db = c.in(b, n2(batch_size, max_length));
+    auto dal = c.in(a_lengths, B); auto dbl = c.in(b_lengths, B);
+    auto od = c.out(distance, B);
+    levenshtein_edit_distance(da, db, dal, dbl, batch_size, max_length, od, c.stream());
+    c.finish();
+}
+
+// ---- lattice forward-backward ----------------------------------------------------------------
+size_t ssnt_tts_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u) {
+    return fb_workspace_bytes(batch_size, max_t, max_u);
+}
+
+void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, const int* t_len,
+                               const int* u_len, int batch_size, int max_t, int max_u,
+                               float* log_likelihood, float* loss, float* grad_emit, float* grad_shift,
+                               void* workspace, size_t workspace_bytes) {
+    NOT_NULL(log_emit); NOT_NULL(log_shift); NOT_NULL(log_likelihood); NOT_NULL(grad_emit); NOT_NULL(grad_shift);
+    if (is_device_pointer(log_emit)) {
+        FbArgs a{log_emit, log_shift, t_len, u_len, batch_size, max_t, max_u, log_likelihood, loss,
+                 grad_emit, grad_shift, workspace, workspace_bytes};
+        launch_forward_backward(a, current_stream());
+        return;
+    }
+    // Host buffers: split the batch into chunks and run H2D(k+1) | kernel(k) | D2H(k-1) on two
+    // auxiliary streams so the PCIe link is busy in both directions.
+    const size_t slab = n2(max_t, max_u);
+    const int B = batch_size > 0 ? batch_size : 0;
+    float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
+    float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
+    float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
+    float* d_gs = (float*)device_scratch(7, B * slab * sizeof(float) + 16);
+    float* d_ll = (float*)device_scratch(8, (size_t)B * sizeof(float) + 16);
+    int* d_tl = (int*)device_scratch(9, (size_t)B * sizeof(int) + 16);
+    int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
+    int nchunks = 1;
+    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 8 ? 4 : 2;
+    const int per = (B + nchunks - 1) / (nchunks > 0 ? nchunks : 1);
+    float* d_loss = (float*)device_scratch(11, 8 * sizeof(float));
+    float* h_loss = (float*)pinned_scratch(0, 8 * sizeof(float));
+    const size_t ws_each = fb_workspace_bytes(per, max_t, max_u);
+    char* ws = (char*)device_scratch(0, ws_each * nchunks);
+    tls_aux.init();
+    cudaStream_t main_stream = current_stream();
+    SSNT_CUDA(cudaEventRecord(tls_aux.start, main_stream));
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
+        if (nb <= 0) break;
+        cudaStream_t s = tls_aux.s[c & 1];
+        if (c < 2) SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
+        const size_t o = (size_t)b0 * slab, nbytes = (size_t)nb * slab * sizeof(float);
+        SSNT_CUDA(cudaMemcpyAsync(d_le + o, log_emit + o, nbytes, cudaMemcpyHostToDevice, s));
+        SSNT_CUDA(cudaMemcpyAsync(d_ls + o, log_shift + o, nbytes, cudaMemcpyHostToDevice, s));
+        if (t_len) SSNT_CUDA(cudaMemcpyAsync(d_tl + b0, t_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (u_len) SSNT_CUDA(cudaMemcpyAsync(d_ul + b0, u_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        FbArgs a{d_le + o, d_ls + o, t_len ? d_tl + b0 : nullptr, u_len ? d_ul + b0 : nullptr, nb, max_t,
+                 max_u, d_ll + b0, d_loss + c, d_ge + o, d_gs + o, ws + (size_t)c * ws_each, ws_each};
+        launch_forward_backward(a, s);
+        SSNT_CUDA(cudaMemcpyAsync(grad_emit + o, d_ge + o, nbytes, cudaMemcpyDeviceToHost, s));
+        SSNT_CUDA(cudaMemcpyAsync(grad_shift + o, d_gs + o, nbytes, cudaMemcpyDeviceToHost, s));
+        SSNT_CUDA(cudaMemcpyAsync(log_likelihood + b0, d_ll + b0, nb * sizeof(float), cudaMemcpyDeviceToHost, s));
+        SSNT_CUDA(cudaMemcpyAsync(h_loss + c, d_loss + c, sizeof(float), cudaMemcpyDeviceToHost, s));
+        used = c + 1;
+    }
+    for (int i = 0; i < 2 && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.s[i]));
+    if (loss) {
+        double acc = 0.0;
+        for (int c = 0; c < used; ++c) acc += (double)h_loss[c];
+        *loss = (float)acc;
+    }
+}
+
+size_t tone_latent_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size) {
+    return tone_fb_workspace_bytes(batch_size, max_t, max_u, tone_class_size);
+}
+
+void tone_latent_forward_backward(const float* log_emit, const float* log_shift, const float* log_tone,
+                                  const int* t_len, const int* u_len, int batch_size, int max_t, int max_u,
+                                  int tone_class_size, float* log_likelihood, float* loss, float* grad_emit,
+                                  float* grad_shift, float* grad_tone, void* workspace, size_t workspace_bytes) {
+    NOT_NULL(log_emit); NOT_NULL(log_shift); NOT_NULL(log_tone); NOT_NULL(log_likelihood);
+    NOT_NULL(grad_emit); NOT_NULL(grad_shift); NOT_NULL(grad_tone);
+    if (is_device_pointer(log_emit)) {
+        ToneFbArgs a{log_emit, log_shift, log_tone, t_len, u_len, batch_size, max_t, max_u, tone_class_size,
+                     log_likelihood, loss, grad_emit, grad_shift, grad_tone, workspace, workspace_bytes};
+        launch_tone_forward_backward(a, current_stream());
+        return;
+    }
+    HostCall c;
+    const size_t cells = n3(batch_size, max_t, max_u) * (size_t)(tone_class_size > 0 ? tone_class_size : 0);
+    const size_t tcells = n3(batch_size, max_u, tone_class_size);
+    const size_t B = (size_t)(batch_size > 0 ? batch_size : 0);
+    auto dle = c.in(log_emit, cells); auto dls = c.in(log_shift, cells); auto dlt = c.in(log_tone, tcells);
+    const int* dtl = t_len ? c.in(t_len, B) : nullptr;
+    const int* dul = u_len ? c.in(u_len, B) : nullptr;
+    float dummy_loss = 0.0f;
+    auto oll = c.out(log_likelihood, B); auto olo = c.out(loss ? loss : &dummy_loss, 1);
+    auto oge = c.out(grad_emit, cells); auto ogs = c.out(grad_shift, cells); auto ogt = c.out(grad_tone, tcells);
+    ToneFbArgs a{dle, dls, dlt, dtl, dul, batch_size, max_t, max_u, tone_class_size, oll, olo, oge, ogs, ogt,
+                 nullptr, 0};
+    launch_tone_forward_backward(a, c.stream());
+    c.finish();
+}
+
+// ---- runtime side channel ----------------------------------------------------------------------
+void ssnt_tts_set_stream(void* cuda_stream) { set_stream((cudaStream_t)cuda_stream); }
+void* ssnt_tts_get_stream(void) { return (void*)current_stream(); }
+void ssnt_tts_set_memory_space(int space) {
+    SSNT_ASSERT(space >= 0 && space <= 2, "ssnt_tts_set_memory_space: 0 auto, 1 host, 2 device");
+    set_space(space);
+}
+void ssnt_tts_synchronize(void) {
+    SSNT_CUDA(cudaStreamSynchronize(current_stream()));
+    check_error_flag_or_panic();
+}
+unsigned ssnt_tts_last_error(void) {
+    SSNT_CUDA(cudaStreamSynchronize(current_stream()));
+    return read_and_clear_error_flag();
+}
+void ssnt_tts_set_fb_kernel(int kind) { fb_force_kernel_kind(kind); }
+int ssnt_tts_get_fb_kernel_used(void) { return fb_last_kernel_kind(); }
+const char* ssnt_tts_backend(void) { return "cuda-sm_100a"; }
+
+}  // extern "C"
+#pragma GCC visibility pop

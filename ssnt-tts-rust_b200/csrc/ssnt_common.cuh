@@ -1,0 +1,104 @@
+// Shared declarations of the sm_100a backend behind the ssnt_tts_c C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+namespace ssnt {
+
+// ---- error handling ---------------------------------------------------------------------
+// The reference reports every precondition failure by panicking (assert!/assert_eq! in
+// ssnt_tts_c/src/lib.rs and src/*.rs), i.e. the process aborts.  We keep that behaviour.
+[[noreturn]] inline void panic(const char* what, const char* file, int line) {
+    std::fprintf(stderr, "ssnt_tts_c: panic: %s (%s:%d)\n", what, file, line);
+    std::fflush(stderr);
+    std::abort();
+}
+#define SSNT_ASSERT(cond, msg)                                   \
+    do {                                                         \
+        if (!(cond)) ::ssnt::panic(msg, __FILE__, __LINE__);      \
+    } while (0)
+#define SSNT_CUDA(call)                                                            \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) ::ssnt::panic(cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Device-side conditions that are a panic in the reference are recorded as bits of a flag word
+// (mapped pinned host memory) and turned into the panic at the next synchronising call.
+enum ErrorBits : unsigned {
+    kErrV2EmptyBeam = 1u,        // src/v2.rs:292 assert_ne!(n_results, 0)
+    kErrUpsampleLength = 2u,     // src/v2_util.rs:58 assert_eq!(upsampled.len(), output_length)
+    kErrToneEmptyBeam = 4u,      // src/tone_latent.rs:199 `i % n_results` with n_results == 0
+    kErrBadIndex = 8u,           // out-of-range parent index in a back-trace table
+};
+
+// ---- runtime (runtime.cu) ------------------------------------------------------------------
+cudaStream_t current_stream();             // thread-local side channel, see ssnt_tts_set_stream
+void set_stream(cudaStream_t s);
+void set_space(int space);
+unsigned* next_done_counter();             // zero-initialised, self-resetting ticket (ring of 1024)
+unsigned* device_error_flag();             // device pointer to the flag word
+unsigned read_and_clear_error_flag();      // host side; caller must have synchronised
+void check_error_flag_or_panic();          // panics with the reference's message if a bit is set
+
+enum MemSpace { kAuto = 0, kHost = 1, kDevice = 2 };
+bool is_device_pointer(const void* p);     // honours ssnt_tts_set_memory_space
+
+// Grow-only per-thread device scratch (workspace the caller did not provide, staging of host
+// buffers).  Slots are independent so one call can hold several live buffers.
+void* device_scratch(int slot, size_t bytes);
+void* pinned_scratch(int slot, size_t bytes);
+int sm_count();
+
+// RAII staging of one host array on the device for the host-pointer flavour of the C-ABI.
+struct Staged {
+    void* dev = nullptr;
+    void* host = nullptr;
+    size_t bytes = 0;
+    bool copy_back = false;
+};
+
+// ---- launchers (one per kernel family; all asynchronous on current_stream()) -----------------
+struct FbArgs {
+    const float* log_emit;
+    const float* log_shift;
+    const int* t_len;   // may be null → max_t
+    const int* u_len;   // may be null → max_u
+    int batch_size, max_t, max_u;
+    float* log_likelihood;  // [B]
+    float* loss;            // [1], may be null
+    float* grad_emit;       // [B,T,U]
+    float* grad_shift;      // [B,T,U]
+    void* workspace;
+    size_t workspace_bytes;
+};
+size_t fb_workspace_bytes(int batch_size, int max_t, int max_u);
+void launch_forward_backward(const FbArgs& a, cudaStream_t stream);
+// Which kernel family the last launch_forward_backward on this thread used (1 = warp/TMA
+// lattice kernel, 0 = generic block kernel); for tests and the bench's launch accounting.
+int fb_last_kernel_kind();
+void fb_force_kernel_kind(int kind);  // -1 auto, 0 generic, 1 warp
+
+struct ToneFbArgs {
+    const float* log_emit;   // [B,T,U,K]
+    const float* log_shift;  // [B,T,U,K]
+    const float* log_tone;   // [B,U,K]
+    const int* t_len;
+    const int* u_len;
+    int batch_size, max_t, max_u, tone_class_size;
+    float* log_likelihood;
+    float* loss;
+    float* grad_emit;
+    float* grad_shift;
+    float* grad_tone;
+    void* workspace;
+    size_t workspace_bytes;
+};
+size_t tone_fb_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
+void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream);
+
+}  // namespace ssnt

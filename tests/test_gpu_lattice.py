@@ -1,0 +1,247 @@
+"""GPU parity of the lattice forward-backward (and its tone-latent variant) against the fp64
+CPU oracle, through the C-ABI.
+
+The reference has no forward-backward at all, so the oracle for this part is
+an authored specification — "parity unpinned" by the reference; the oracle itself is hardened in
+test_oracle_lattice.py.  Tolerances (BASELINE.json north_star): log-likelihood within 1e-5
+relative; gradients within 1e-4 relative, measured against the largest occupancy of the
+utterance (gradients are posterior probabilities in [0, 1]; element-wise relative error of
+entries like 1e-30 is not meaningful in fp32).  Full-size runs are additionally checked through
+size-independent properties: every frame's occupancies sum to 1, expected shifts = U-1."""
+import numpy as np
+import pytest
+
+from lattice_util import make_inputs, ragged_lengths
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _dev(x):
+    import torch
+    return None if x is None else torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+def _check(got, want, t_len=None, u_len=None):
+    ll, loss, ge, gs = (_np(g) for g in got)
+    ll64, loss64, ge64, gs64 = want
+    finite = np.isfinite(ll64)
+    assert np.array_equal(np.isfinite(ll), finite)
+    assert np.all(np.abs(ll[finite] - ll64[finite]) <= LL_RTOL * np.abs(ll64[finite]) + 1e-6)
+    if finite.all():
+        assert abs(float(loss[0]) - loss64) <= LL_RTOL * abs(loss64) + 1e-5
+    for b in range(ll.shape[0]):
+        for g, g64 in ((ge[b], ge64[b]), (gs[b], gs64[b])):
+            scale = max(float(np.abs(ge64[b]).max()), 1e-30)
+            err = float(np.abs(g - g64).max())
+            assert err <= GRAD_RTOL * scale, (b, err, scale)
+        # padded / unreachable cells are exactly zero
+        assert not ge[b][ge64[b] == 0].any() or np.abs(ge[b][ge64[b] == 0]).max() <= GRAD_RTOL
+        if t_len is not None:
+            assert not ge[b, t_len[b]:].any() and not gs[b, t_len[b]:].any()
+            assert not ge[b, :, u_len[b]:].any() and not gs[b, :, u_len[b]:].any()
+
+
+def _run(product, le, ls, t_len, u_len, space, kind=-1):
+    product.set_fb_kernel(kind)
+    try:
+        if space == "device":
+            out = product.forward_backward(_dev(le), _dev(ls), _dev(t_len), _dev(u_len))
+        else:
+            out = product.forward_backward(le, ls, t_len, u_len)
+        used = product.fb_kernel_used()
+    finally:
+        product.set_fb_kernel(-1)
+    return out, used
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_config1_B1_U32_T120(product, oracle_mod, space):
+    # BASELINE configs[0]: the reference's own CPU-runnable shape
+    le, ls = make_inputs(1, 120, 32, seed=1234)
+    want = oracle_mod.forward_backward(le, ls)
+    got, used = _run(product, le, ls, None, None, space)
+    assert used == 1  # the warp/TMA kernel, not the generic fallback
+    _check(got, want)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("B,T,U", [(3, 1, 4), (2, 2, 4), (4, 3, 4), (5, 9, 8), (3, 17, 16), (2, 40, 36),
+                                   (3, 64, 64), (2, 100, 128), (2, 70, 200), (1, 90, 260), (1, 600, 520)])
+def test_shapes_and_ragged_lengths(product, oracle_mod, kind, B, T, U):
+    le, ls = make_inputs(B, T, U, seed=T * 1000 + U)
+    rng = np.random.default_rng(T + U)
+    t_len = rng.integers(1, T + 1, B).astype(np.int32)
+    u_len = np.array([rng.integers(1, min(U, tb) + 1) for tb in t_len], np.int32)
+    t_len[0] = T
+    u_len[0] = min(U, T)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, used = _run(product, le, ls, t_len, u_len, "device", kind)
+    assert used == kind
+    _check(got, want, t_len, u_len)
+
+
+@pytest.mark.parametrize("U", [1, 5, 30, 33, 150])
+def test_unaligned_max_u_takes_generic_kernel(product, oracle_mod, U):
+    le, ls = make_inputs(3, 47, U, seed=U)
+    t_len, u_len = ragged_lengths(3, 47, U, seed=U)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, used = _run(product, le, ls, t_len, u_len, "device")
+    assert used == (1 if U % 4 == 0 else 0)
+    _check(got, want, t_len, u_len)
+
+
+def test_infeasible_empty_and_masked(product, oracle_mod):
+    le, ls = make_inputs(6, 12, 8, seed=5)
+    t_len = np.array([12, 0, 3, 12, 1, 12], np.int32)
+    u_len = np.array([8, 2, 5, 0, 1, 8], np.int32)   # 1: T=0, 2: U>T, 3: U=0 → ll=-inf, grads 0
+    le[5, 4, :] = -np.inf                            # frame 4 cannot emit anywhere …
+    ls[5, 4, :] = -np.inf                            # … nor shift: no path at all → -inf
+    le[0, 3, 2] = -np.inf                            # a single forbidden cell is fine
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    assert np.isneginf(want[0][[1, 2, 3, 5]]).all() and np.isfinite(want[0][[0, 4]]).all()
+    for kind in (0, 1):
+        got, _ = _run(product, le, ls, t_len, u_len, "device", kind)
+        _check(got, want, t_len, u_len)
+        assert np.isposinf(_np(got[1])[0])
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_config2_B32_U128_T800(product, oracle_mod, space):
+    # BASELINE configs[1]: the headline shape, full lengths
+    le, ls = make_inputs(32, 800, 128, seed=1234)
+    want = oracle_mod.forward_backward(le, ls)
+    got, used = _run(product, le, ls, None, None, space)
+    assert used == 1
+    _check(got, want)
+    ll, loss, ge, gs = (_np(g) for g in got)
+    rows = (ge + gs).sum(axis=2)
+    np.testing.assert_allclose(rows, 1.0, atol=2e-4)          # one transition per frame
+    np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)  # exactly U-1 shifts
+
+
+def test_config2_ragged(product, oracle_mod):
+    le, ls = make_inputs(32, 800, 128, seed=77)
+    t_len, u_len = ragged_lengths(32, 800, 128)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, _ = _run(product, le, ls, t_len, u_len, "device")
+    _check(got, want, t_len, u_len)
+
+
+def test_peaked_and_uniform_inputs(product, oracle_mod):
+    """Inputs that stress the dynamic range: exactly uniform probabilities (binomial spread of
+    alpha over hundreds of bits) and a sharply peaked, mostly-wrong model (log-probs of -30)."""
+    B, T, U = 4, 400, 64
+    le = np.full((B, T, U), np.log(0.5), np.float32)
+    ls = np.full((B, T, U), np.log(0.5), np.float32)
+    rng = np.random.default_rng(3)
+    le[1] = -30.0 * (rng.random((T, U)) < 0.5) - 1e-3
+    ls[1] = -30.0 * (rng.random((T, U)) < 0.5) - 1e-3
+    le[2], ls[2] = np.log(1e-10), np.log1p(-1e-10)        # model insists on shifting every frame
+    le[3], ls[3] = np.log1p(-1e-6), np.log(1e-6)          # model never wants to shift
+    want = oracle_mod.forward_backward(le, ls)
+    for kind in (0, 1):
+        got, _ = _run(product, le, ls, None, None, "device", kind)
+        _check(got, want)
+
+
+def test_large_batch_properties(product):
+    """Size-independent invariants at a batch far beyond what the CPU oracle covers in seconds:
+    B=1024 U=128 T=400 (more CTAs than the GPU holds at once, multi-wave), ragged."""
+    import torch
+    B, T, U = 1024, 400, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.randn(B, T, U, device="cuda", generator=g)
+    le = torch.nn.functional.logsigmoid(z)
+    ls = torch.nn.functional.logsigmoid(-z)
+    t_len = torch.randint(240, T + 1, (B,), device="cuda", generator=g, dtype=torch.int32)
+    u_len = torch.randint(77, U + 1, (B,), device="cuda", generator=g, dtype=torch.int32)
+    ll, loss, ge, gs = product.forward_backward(le, ls, t_len, u_len)
+    torch.cuda.synchronize()
+    rows = (ge + gs).sum(dim=2)
+    valid = torch.arange(T, device="cuda")[None, :] < t_len[:, None]
+    assert torch.allclose(rows[valid], torch.ones_like(rows[valid]), atol=2e-4)
+    assert not rows[~valid].any()
+    assert torch.allclose(gs.sum(dim=(1, 2)), (u_len - 1).float(), rtol=1e-4)
+    assert torch.allclose(loss[0], -ll.double().sum().float(), rtol=1e-6)
+    # linearity of the likelihood in a per-utterance constant: adding c to every log_emit of the
+    # last frame adds exactly c to ll and leaves the occupancies unchanged
+    le2 = le.clone()
+    idx = (t_len - 1).long()
+    le2[torch.arange(B), idx] += 0.75
+    ll2, _, ge2, _ = product.forward_backward(le2, ls, t_len, u_len)
+    assert torch.allclose(ll2, ll + 0.75, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(ge2, ge, atol=2e-5)
+
+
+def test_repeatable_bitwise(product):
+    le, ls = make_inputs(8, 200, 64, seed=2)
+    a = product.forward_backward(_dev(le), _dev(ls))
+    b = product.forward_backward(_dev(le), _dev(ls))
+    for x, y in zip(a, b):
+        assert np.array_equal(_np(x).view(np.uint32), _np(y).view(np.uint32))
+
+
+def test_caller_workspace_and_preallocated_outputs(product, oracle_mod):
+    import torch
+    le, ls = make_inputs(4, 64, 32, seed=6)
+    want = oracle_mod.forward_backward(le, ls)
+    n = product.forward_backward_workspace_bytes(4, 64, 32)
+    ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    out = (torch.empty(4, device="cuda"), torch.empty(1, device="cuda"),
+           torch.full((4, 64, 32), 7.0, device="cuda"), torch.full((4, 64, 32), 7.0, device="cuda"))
+    got = product.forward_backward(_dev(le), _dev(ls), workspace=ws, out=out)
+    _check(got, want)
+
+
+# ---------------------------------------------------------------- tone-latent lattice
+def _check_tone(got, want):
+    ll, loss, ge, gs, gt = (_np(g) for g in got)
+    ll64, loss64, ge64, gs64, gt64 = want
+    finite = np.isfinite(ll64)
+    assert np.array_equal(np.isfinite(ll), finite)
+    assert np.all(np.abs(ll[finite] - ll64[finite]) <= LL_RTOL * np.abs(ll64[finite]) + 1e-6)
+    for b in range(ll.shape[0]):
+        scale = max(float(np.abs(ge64[b]).max()), 1e-30)
+        for g, g64 in ((ge[b], ge64[b]), (gs[b], gs64[b]), (gt[b], gt64[b])):
+            assert float(np.abs(g - g64).max()) <= GRAD_RTOL * max(scale, float(np.abs(g64).max()))
+
+
+@pytest.mark.parametrize("space", ["host", "device"])
+@pytest.mark.parametrize("B,T,U,K", [(2, 1, 1, 3), (3, 12, 5, 2), (4, 60, 24, 4), (2, 33, 9, 1), (2, 50, 40, 7)])
+def test_tone_latent_small(product, oracle_mod, space, B, T, U, K):
+    le, ls, lt = make_inputs(B, T, U, seed=T + U + K, K=K)
+    t_len, u_len = ragged_lengths(B, T, U, seed=K)
+    t_len[0], u_len[0] = T, min(T, U)
+    want = oracle_mod.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    if space == "device":
+        got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
+    else:
+        got = product.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    _check_tone(got, want)
+
+
+def test_tone_latent_config3_B32_U128_T800_K4(product, oracle_mod):
+    # BASELINE configs[2]
+    le, ls, lt = make_inputs(32, 800, 128, seed=1234, K=4)
+    want = oracle_mod.tone_latent_forward_backward(le, ls, lt)
+    got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt))
+    _check_tone(got, want)
+    ll, loss, ge, gs, gt = (_np(g) for g in got)
+    np.testing.assert_allclose((ge + gs).sum(axis=(2, 3)), 1.0, atol=3e-4)
+    np.testing.assert_allclose(gt.sum(axis=2), 1.0, atol=3e-4)
+
+
+def test_tone_latent_infeasible(product, oracle_mod):
+    le, ls, lt = make_inputs(3, 6, 8, seed=9, K=2)
+    t_len, u_len = np.array([6, 0, 4], np.int32), np.array([7, 3, 4], np.int32)
+    want = oracle_mod.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
+    _check_tone(got, want)
+    assert np.isneginf(_np(got[0])[:2]).all()
