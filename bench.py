@@ -90,7 +90,9 @@ def synthetic_torch(b0, B, T, U, device, seed=1234):
         x = (x ^ (x >> 27)) * -7723592293110705685      # 0x94D049BB133111EB as int64
         return x ^ (x >> 31)
 
-    k = idx * 2 + seed * -7046029254386353131           # 0x9E3779B97F4A7C15 as int64
+    off = (seed * 0x9E3779B97F4A7C15) & ((1 << 64) - 1)
+    off = off - (1 << 64) if off >= (1 << 63) else off   # two's-complement int64
+    k = idx * 2 + off
     u1 = ((mix(k) >> 11) & ((1 << 53) - 1)).double() / float(1 << 53)
     u2 = ((mix(k + 1) >> 11) & ((1 << 53) - 1)).double() / float(1 << 53)
     z = (torch.sqrt(-2.0 * torch.log(u1 + 1e-300)) * torch.cos(2.0 * torch.pi * u2)).float()
