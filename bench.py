@@ -221,6 +221,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     P = load_product()
     P.lib()
+    P.set_fb_kernel(args.fb_kernel)
     B, T, U = WORKLOADS[args.workload]
     cells = B * T * U
     set_bytes = cells * 4 * 4 + P.forward_backward_workspace_bytes(B, T, U)
@@ -340,7 +341,9 @@ def run_b200(args):
             "global_batch": world * B, "parallelism": f"batch-sharded dp{world}, all-reduce of the scalar loss only",
             "l2_policy": f"rotating {nsets} independent input/output/scratch sets "
                          f"({nsets * set_bytes / 1e6:.0f} MB > 3x 126 MB L2); inputs come from HBM every step",
-            "fb_kernel": {1: "fb_warp_kernel (cluster of 2 warps, TMA ring)", 0: "fb_generic_kernel"}.get(kernel_kind),
+            "fb_kernel": {2: "fb_bf_kernel (block-float, warp-specialised cluster of 2 CTAs, TMA ring)",
+                          1: "fb_log_warp_kernel (log domain, cluster of 2 warps, TMA ring)",
+                          0: "fb_generic_kernel"}.get(kernel_kind),
             "loss_check": final_loss,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -378,6 +381,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fb-kernel", type=int, default=-1, help="-1 auto, 0 generic, 1 log-warp, 2 block-float")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -140,7 +140,8 @@ void ssnt_tts_synchronize(void);
  * 1 = v2 empty beam (src/v2.rs:292), 2 = upsample length mismatch (src/v2_util.rs:58),
  * 4 = tone-latent empty beam, 8 = back-trace index out of range. */
 unsigned ssnt_tts_last_error(void);
-/* Forward-backward kernel selection for tests/benchmarks: -1 auto, 0 generic, 1 warp/TMA. */
+/* Forward-backward kernel selection for tests/benchmarks: -1 auto, 0 generic, 1 log-domain
+ * warp/TMA, 2 block-float warp-specialised (default hot path), 3 = 2 with forced log re-run. */
 void ssnt_tts_set_fb_kernel(int kind);
 int ssnt_tts_get_fb_kernel_used(void);
 const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */

@@ -145,7 +145,9 @@ class _Call:
 
 
 def set_fb_kernel(kind: int) -> None:
-    """-1 auto, 0 generic block kernel, 1 warp/TMA cluster kernel (tests and benchmarks)."""
+    """-1 auto, 0 generic block kernel, 1 log-domain warp/TMA cluster kernel, 2 block-float
+    warp-specialised kernel (the default hot path), 3 = 2 with the log-domain re-run forced
+    (tests and benchmarks)."""
     lib().ssnt_tts_set_fb_kernel(c_int(kind))
 
 

@@ -6,12 +6,14 @@
 // (T-1, U-1)).  T = output frames (serial), U = input tokens (across lanes).
 //
 // Kernels (selected by launch_forward_backward):
+//  * kind 2  fb_bf_kernel<CPL>        the hot path: warp-specialised block-floating-point recursion
+//            (fb_bf.cuh) with an in-kernel log-domain re-run of utterances it cannot hold.
 //  * kind 1  fb_log_warp_kernel<CPL>  cluster of two single-warp CTAs per utterance, log2 domain
 //            with per-lane offsets, TMA-fed ring (fb_log_warp.cuh).  Numerically unconditional.
 //  * kind 0  fb_generic_kernel        any shape/alignment (max_u % 4 != 0, U > 1024, unaligned
 //            bases): one CTA per utterance, one thread per token, rows in shared memory, log2
 //            domain with one integer offset per token.
-#include "fb_log_warp.cuh"
+#include "fb_bf.cuh"
 
 namespace ssnt {
 namespace {
@@ -45,6 +47,54 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
                              reinterpret_cast<float*>(smem_raw + 128), cluster);
     }
     if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, lane, 32);
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(kBfThreads) fb_bf_kernel(const BfParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();  // 0 = alpha sweep, 1 = beta sweep
+    const int b = blockIdx.x >> 1;
+    const FbArgs& a = p.a;
+    int T = a.t_len ? a.t_len[b] : a.max_t;
+    int U = a.u_len ? a.u_len[b] : a.max_u;
+    T = min(max(T, 0), a.max_t);
+    U = min(max(U, 0), a.max_u);
+    const size_t slab = (size_t)a.max_t * a.max_u;
+    if (T <= 0 || U <= 0 || U > T) {
+        // No monotonic path: ll = -inf, every gradient 0.  Uniform for both CTAs of the cluster.
+        float4* g = reinterpret_cast<float4*>((rank == 0 ? a.grad_emit : a.grad_shift) + (size_t)b * slab);
+        for (size_t i = tid; i < slab / 4; i += kBfThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (rank == 0 && tid == 0) a.log_likelihood[b] = -INFINITY;
+    } else {
+        bf_lattice_cta<CPL>(p, b, rank, T, U, smem_raw, cluster);
+        // Padded frames t >= T (rank 0 clears grad_emit, rank 1 grad_shift).
+        {
+            float4* g = reinterpret_cast<float4*>((rank == 0 ? a.grad_emit : a.grad_shift) + (size_t)b * slab +
+                                                  (size_t)T * a.max_u);
+            const size_t n4 = (size_t)(a.max_t - T) * a.max_u / 4;
+            for (size_t i = tid; i < n4; i += kBfThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        // Did either CTA flag the utterance?  If so the same cluster redoes it in the log domain.
+        cluster.sync();
+        const unsigned st = *reinterpret_cast<volatile unsigned*>(p.status + b);
+        if (st) {
+            if (warp == 0) {
+                LogParams lp;
+                lp.a = a;
+                lp.scratch = p.scratch;
+                lp.SU = p.SU;
+                lp.NS = p.NS;
+                lp.counter = p.counter;
+                log_lattice_cta<CPL>(lp, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw + 320),
+                                     reinterpret_cast<float*>(smem_raw + 384), cluster);
+            } else {
+                cluster.sync();
+            }
+        }
+    }
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kBfThreads);
 }
 
 // ===============================================================================================
@@ -181,6 +231,28 @@ void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream) {
     SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_log_warp_kernel<CPL>, p));
 }
 
+template <int CPL>
+void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(fb_bf_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)p.a.batch_size * 2u);
+    cfg.blockDim = dim3(kBfThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_bf_kernel<CPL>, p));
+}
+
 inline int round_up4(int x) { return (x + 3) & ~3; }
 
 }  // namespace
@@ -190,7 +262,7 @@ inline int round_up4(int x) { return (x + 3) & ~3; }
 size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     if (B <= 0 || max_t <= 0 || max_u <= 0) return 256;
     const size_t SU = (size_t)round_up4(max_u) + 32;
-    size_t warp_bytes = (size_t)B * (max_t + 1) * SU * sizeof(float);
+    size_t warp_bytes = (size_t)B * (max_t + 1) * SU * sizeof(float) + (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
     size_t gen_bytes = (size_t)2 * B * max_t * max_u * sizeof(float);
     size_t n = warp_bytes > gen_bytes ? warp_bytes : gen_bytes;
     return (n + 255) & ~(size_t)255;
@@ -226,10 +298,35 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
     bool warp_ok = (a.max_u % 4 == 0) && a.max_u <= 1024 && aligned16(a.log_emit) &&
                    aligned16(a.log_shift) && aligned16(a.grad_emit) && aligned16(a.grad_shift) &&
                    aligned16(ws);
+    const bool bf_ok = warp_ok && a.max_u <= 512;
     int kind = tls_force_kind;
-    if (kind < 0) kind = warp_ok ? 1 : 0;
+    if (kind < 0) kind = bf_ok ? 2 : (warp_ok ? 1 : 0);
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
+    if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");
     tls_last_kind = kind;
+
+    if (kind >= 2) {
+        BfParams p;
+        p.a = a;
+        p.scratch = (float*)ws;
+        p.SU = round_up4(a.max_u) + 32;
+        p.status = (unsigned*)((char*)ws + (size_t)a.batch_size * (a.max_t + 1) * p.SU * sizeof(float));
+        p.force_fallback = kind == 3 ? 1 : 0;  // kind 3: run the block-float kernel but force the log-domain re-run
+        p.counter = counter;
+        const size_t stage_bytes = ((size_t)kG * (3 * a.max_u + p.SU) + 32) * sizeof(float);
+        int NS = (int)((size_t)(200 * 1024) / stage_bytes);
+        NS = NS > 8 ? 8 : NS;
+        SSNT_ASSERT(NS >= 3, "forward_backward: ring does not fit shared memory");
+        p.NS = NS;
+        const size_t smem = 384 + (size_t)NS * stage_bytes;
+        const int U = a.max_u;
+        if (U <= 32) launch_bf<1>(p, smem, stream);
+        else if (U <= 64) launch_bf<2>(p, smem, stream);
+        else if (U <= 128) launch_bf<4>(p, smem, stream);
+        else if (U <= 256) launch_bf<8>(p, smem, stream);
+        else launch_bf<16>(p, smem, stream);
+        return;
+    }
 
     if (kind == 1) {
         LogParams p;
