@@ -144,6 +144,12 @@ unsigned ssnt_tts_last_error(void);
  * warp/TMA, 2 block-float warp-specialised (default hot path), 3 = 2 with forced log re-run. */
 void ssnt_tts_set_fb_kernel(int kind);
 int ssnt_tts_get_fb_kernel_used(void);
+/* Cumulative number of utterances the block-float kernel had to re-run in the log domain
+ * because their dynamic range did not fit (waits for the current stream). */
+unsigned ssnt_tts_fb_fallback_count(void);
+/* Profiling aid: device buffer of (2*B*8*16 + 4096) int64 that the block-float kernel fills with per-warp
+ * cycle counters (total, and cycles blocked on each hand-off barrier); NULL switches it off. */
+void ssnt_tts_debug_set_fb_stats(void *dev_buffer);
 const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
 
 #ifdef __cplusplus

@@ -47,6 +47,8 @@ C_SYMBOLS = (
     "ssnt_tts_last_error",
     "ssnt_tts_set_fb_kernel",
     "ssnt_tts_get_fb_kernel_used",
+    "ssnt_tts_fb_fallback_count",
+    "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
 )
 
@@ -84,6 +86,7 @@ def lib() -> ctypes.CDLL:
         L.ssnt_tts_set_stream.argtypes = [c_void_p]
         L.ssnt_tts_last_error.restype = c_uint
         L.ssnt_tts_get_fb_kernel_used.restype = c_int
+        L.ssnt_tts_fb_fallback_count.restype = c_uint
         L.ssnt_tts_backend.restype = ctypes.c_char_p
         _lib = L
     return _lib
@@ -153,6 +156,11 @@ def set_fb_kernel(kind: int) -> None:
 
 def fb_kernel_used() -> int:
     return int(lib().ssnt_tts_get_fb_kernel_used())
+
+
+def fb_fallback_count() -> int:
+    """Cumulative number of utterances the block-float kernel re-ran in the log domain."""
+    return int(lib().ssnt_tts_fb_fallback_count())
 
 
 def synchronize() -> None:

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-fmad=true",
-]
+] + (["-DSSNT_BF_DEBUG_VARIANTS"] if os.environ.get("SSNT_BF_DEBUG_VARIANTS") else [])
 
 
 def _nvcc() -> str:
@@ -37,8 +37,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(CSRC, "ssnt_common.cuh"),
-                        os.path.join(HERE, "..", "include", "ssnt_tts_c.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ssnt_tts_c.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

@@ -22,6 +22,7 @@ using namespace lattice;
 
 thread_local int tls_force_kind = -1;
 thread_local int tls_last_kind = -1;
+thread_local long long* tls_stats = nullptr;
 
 template <int CPL>
 __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
@@ -80,15 +81,16 @@ __global__ void __launch_bounds__(kBfThreads) fb_bf_kernel(const BfParams p) {
         cluster.sync();
         const unsigned st = *reinterpret_cast<volatile unsigned*>(p.status + b);
         if (st) {
+            if (rank == 0 && tid == 0) atomicAdd(p.fallbacks, 1u);
             if (warp == 0) {
                 LogParams lp;
                 lp.a = a;
                 lp.scratch = p.scratch;
                 lp.SU = p.SU;
-                lp.NS = p.NS;
+                lp.NS = p.NS < 8 ? p.NS : 8;
                 lp.counter = p.counter;
-                log_lattice_cta<CPL>(lp, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw + 320),
-                                     reinterpret_cast<float*>(smem_raw + 384), cluster);
+                log_lattice_cta<CPL>(lp, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw + 576),
+                                     reinterpret_cast<float*>(smem_raw + kBfHeaderBytes), cluster);
             } else {
                 cluster.sync();
             }
@@ -269,6 +271,7 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
 }
 
 int fb_last_kernel_kind() { return tls_last_kind; }
+void fb_set_stats_buffer(long long* dev) { tls_stats = dev; }
 void fb_force_kernel_kind(int kind) { tls_force_kind = kind; }
 
 void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
@@ -298,7 +301,7 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
     bool warp_ok = (a.max_u % 4 == 0) && a.max_u <= 1024 && aligned16(a.log_emit) &&
                    aligned16(a.log_shift) && aligned16(a.grad_emit) && aligned16(a.grad_shift) &&
                    aligned16(ws);
-    const bool bf_ok = warp_ok && a.max_u <= 512;
+    const bool bf_ok = warp_ok && a.max_u <= 256;
     int kind = tls_force_kind;
     if (kind < 0) kind = bf_ok ? 2 : (warp_ok ? 1 : 0);
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
@@ -311,20 +314,29 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         p.scratch = (float*)ws;
         p.SU = round_up4(a.max_u) + 32;
         p.status = (unsigned*)((char*)ws + (size_t)a.batch_size * (a.max_t + 1) * p.SU * sizeof(float));
+        p.fallbacks = device_fallback_counter();
         p.force_fallback = kind == 3 ? 1 : 0;  // kind 3: run the block-float kernel but force the log-domain re-run
         p.counter = counter;
+        p.stats = tls_stats;
         const size_t stage_bytes = ((size_t)kG * (3 * a.max_u + p.SU) + 32) * sizeof(float);
-        int NS = (int)((size_t)(200 * 1024) / stage_bytes);
-        NS = NS > 8 ? 8 : NS;
-        SSNT_ASSERT(NS >= 3, "forward_backward: ring does not fit shared memory");
+        int NS = (int)((size_t)(224 * 1024 - kBfHeaderBytes) / stage_bytes);
+        NS = NS > 12 ? 12 : NS;
+        SSNT_ASSERT(NS >= 4, "forward_backward: ring does not fit shared memory");
         p.NS = NS;
-        const size_t smem = 384 + (size_t)NS * stage_bytes;
+        // Few utterances (latency mode): one CTA per SM has to cover the whole HBM latency by
+        // itself, so prefetch far ahead; many utterances: neighbours share the L2, stay modest.
+        p.pf_rows = (size_t)a.batch_size * 2 <= (size_t)sm_count() ? 256 : 64;
+        if (const char* e = std::getenv("SSNT_BF_PF_ROWS")) p.pf_rows = std::atoi(e);  // tuning aid
+        p.pf_sleep_ns = 64;
+        if (const char* e = std::getenv("SSNT_BF_SLEEP_NS")) p.pf_sleep_ns = std::atoi(e);  // tuning aid
+        p.debug_skip = 0;
+        if (const char* e = std::getenv("SSNT_BF_DEBUG_SKIP")) p.debug_skip = std::atoi(e);  // profiling aid
+        const size_t smem = kBfHeaderBytes + (size_t)NS * stage_bytes;
         const int U = a.max_u;
         if (U <= 32) launch_bf<1>(p, smem, stream);
         else if (U <= 64) launch_bf<2>(p, smem, stream);
         else if (U <= 128) launch_bf<4>(p, smem, stream);
-        else if (U <= 256) launch_bf<8>(p, smem, stream);
-        else launch_bf<16>(p, smem, stream);
+        else launch_bf<8>(p, smem, stream);
         return;
     }
 

@@ -149,7 +149,7 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
         for (int k = 0; k < nst; ++k) {
             const unsigned kk = kg + (unsigned)k;
             const int slot = (int)(kk % (unsigned)NS);
-            mbar_wait(smem_u32(bars + slot), (kk / (unsigned)NS) & 1u);
+            mbar_wait_warp(smem_u32(bars + slot), (kk / (unsigned)NS) & 1u);  // warp-uniform: stays converged
             const float* st = ring + (size_t)slot * stage_floats;
             const int j0 = k * kG;
             const int cnt = min(kG, n - j0);
@@ -209,7 +209,7 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
         for (int k = 0; k < nst; ++k) {
             const unsigned kk = kg + (unsigned)k;
             const int slot = (int)(kk % (unsigned)NS);
-            mbar_wait(smem_u32(bars + slot), (kk / (unsigned)NS) & 1u);
+            mbar_wait_warp(smem_u32(bars + slot), (kk / (unsigned)NS) & 1u);  // warp-uniform: stays converged
             const float* st = ring + (size_t)slot * stage_floats;
             const int j0 = k * kG;
             const int cnt = min(kG, n - j0);

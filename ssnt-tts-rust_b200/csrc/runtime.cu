@@ -24,15 +24,15 @@ thread_local Scratch tls_pin[kSlots];
 
 std::once_flag g_flag_once;
 unsigned* g_flag_host = nullptr;  // mapped pinned word
-unsigned* g_flag_dev = nullptr;
+unsigned* g_flag_dev = nullptr;  // [0] error bits, [1] count of utterances re-run in the log domain
 int g_sm_count = 0;
 constexpr int kCounters = 1024;
 unsigned* g_counters = nullptr;  // device, zeroed once; each user resets its ticket to 0
 std::atomic<unsigned> g_next_counter{0};
 
 void init_flag() {
-    SSNT_CUDA(cudaHostAlloc((void**)&g_flag_host, sizeof(unsigned), cudaHostAllocMapped));
-    *g_flag_host = 0;
+    SSNT_CUDA(cudaHostAlloc((void**)&g_flag_host, 4 * sizeof(unsigned), cudaHostAllocMapped));
+    g_flag_host[0] = g_flag_host[1] = g_flag_host[2] = g_flag_host[3] = 0;
     SSNT_CUDA(cudaHostGetDevicePointer((void**)&g_flag_dev, g_flag_host, 0));
     int dev = 0;
     SSNT_CUDA(cudaGetDevice(&dev));
@@ -60,6 +60,16 @@ unsigned* next_done_counter() {
 int sm_count() {
     std::call_once(g_flag_once, init_flag);
     return g_sm_count;
+}
+
+unsigned* device_fallback_counter() {
+    std::call_once(g_flag_once, init_flag);
+    return g_flag_dev + 1;
+}
+
+unsigned read_fallback_counter() {
+    std::call_once(g_flag_once, init_flag);
+    return ((volatile unsigned*)g_flag_host)[1];
 }
 
 unsigned read_and_clear_error_flag() {

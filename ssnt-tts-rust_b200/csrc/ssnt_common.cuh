@@ -43,6 +43,8 @@ void set_space(int space);
 unsigned* next_done_counter();             // zero-initialised, self-resetting ticket (ring of 1024)
 unsigned* device_error_flag();             // device pointer to the flag word
 unsigned read_and_clear_error_flag();      // host side; caller must have synchronised
+unsigned* device_fallback_counter();       // utterances the block-float kernel re-ran in the log domain
+unsigned read_fallback_counter();          // host side, cumulative
 void check_error_flag_or_panic();          // panics with the reference's message if a bit is set
 
 enum MemSpace { kAuto = 0, kHost = 1, kDevice = 2 };
@@ -81,7 +83,8 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream);
 // Which kernel family the last launch_forward_backward on this thread used (1 = warp/TMA
 // lattice kernel, 0 = generic block kernel); for tests and the bench's launch accounting.
 int fb_last_kernel_kind();
-void fb_force_kernel_kind(int kind);  // -1 auto, 0 generic, 1 warp
+void fb_force_kernel_kind(int kind);  // -1 auto, 0 generic, 1 log-warp, 2 block-float, 3 = 2 + forced re-run
+void fb_set_stats_buffer(long long* dev);  // profiling aid for the block-float kernel (null = off)
 
 struct ToneFbArgs {
     const float* log_emit;   // [B,T,U,K]

@@ -81,8 +81,8 @@ def test_shapes_and_ragged_lengths(product, oracle_mod, kind, B, T, U):
     u_len = np.array([rng.integers(1, min(U, tb) + 1) for tb in t_len], np.int32)
     t_len[0] = T
     u_len[0] = min(U, T)
-    if kind >= 2 and U > 512:
-        pytest.skip("block-float kernel covers max_u <= 512; larger lattices take the log-warp kernel")
+    if kind >= 2 and U > 256:
+        pytest.skip("block-float kernel covers max_u <= 256; larger lattices take the log-warp kernel")
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     got, used = _run(product, le, ls, t_len, u_len, "device", kind)
     assert used == kind

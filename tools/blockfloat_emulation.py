@@ -31,6 +31,10 @@ def scale_pow2(v, k):
     return (v * pow2(k1)[..., None]).astype(f32) * pow2(k - k1)[..., None]
 
 
+PIPELINED = True
+DEC_AT = 6   # the decision is taken from the state before this row of the stage, applied at the next stage start
+
+
 def sweep(e, s, U, CPL, direction):
     """Runs one full sweep (all T rows) and returns the list of (v[lanes,CPL], exp[lanes]) per row
     BEFORE the step of that row.  direction=+1: alpha from row 0; -1: beta from row T-1 (state of
@@ -48,10 +52,34 @@ def sweep(e, s, U, CPL, direction):
     else:
         v[(U - 1) // CPL, (U - 1) % CPL] = 1
     g = np.ones(L, f32)
+    if direction > 0: g[0] = 0
+    else: g[-1] = 0
+    dec = None
     rows = []
     order = range(T) if direction > 0 else range(T - 1, -1, -1)
     for j, t in enumerate(order):
-        if j % G == 0:
+        if j % G == 0 and PIPELINED:
+            if dec is not None:
+                new = dec
+                v = scale_pow2(v, ex - new)
+                ex = new
+                d = np.zeros(L, np.int64)
+                if direction > 0: d[1:] = ex[:-1] - ex[1:]
+                else: d[:-1] = ex[1:] - ex[:-1]
+                g = pow2(np.clip(d, -126, 126))
+                if direction > 0: g[0] = 0
+                else: g[-1] = 0
+        if j % G == DEC_AT and PIPELINED:
+            mloc = v.max(axis=1)
+            own = np.where(mloc > 0, ex + ilogb(np.maximum(mloc, f32(1e-45))) - TARGET, BIG)
+            edge = v[:, -1] if direction > 0 else v[:, 0]
+            amag = np.where(edge > 0, ex + ilogb(np.maximum(edge, f32(1e-45))), BIG)
+            nb = np.full(L, BIG, np.int64)
+            if direction > 0: nb[1:] = amag[:-1]
+            else: nb[:-1] = amag[1:]
+            new = np.maximum(own, nb - TARGET - SLACK)
+            dec = np.where(new <= BIG // 2, ex, new)
+        if j % G == 0 and not PIPELINED:
             # ---- renorm ----
             mloc = v.max(axis=1)
             own = np.where(mloc > 0, ex + ilogb(np.maximum(mloc, f32(1e-45))) - TARGET, BIG)
