@@ -35,7 +35,8 @@ namespace ssnt {
 namespace lattice {
 
 constexpr int kTarget = 24;       // lane maximum is scaled to ~2^kTarget at every re-normalisation
-constexpr int kSlack = 32;        // a lane's frame may sit this far below its feeding neighbour's edge
+constexpr int kSlack = 0;         // a lane's frame never sits below its feeding neighbour's edge: what arrives lands at <= 2^kTarget
+                                  // when decided, leaving ~100 bits for its growth until the next decision
 constexpr float kBfConsistency = 2e-5f;  // the three likelihood estimates must agree this well (typ. 1e-6)
 constexpr int kNoMass = -100000;  // exponent key of an all-zero lane
 constexpr int kBfHeaderBytes = 768;  // mbarriers (512) | llinfo (64) | log-domain re-run barriers (128) | pad
@@ -106,31 +107,6 @@ __device__ __forceinline__ float scale_pow2(float x, int k) {
     return (x * pow2i(k1)) * pow2i(k - k1);
 }
 
-// Re-normalisation of one lane at a stage boundary.  DIR=+1: alpha (fed by lane-1's last cell),
-// DIR=-1: beta (fed by lane+1's first cell).  Returns the factor g = 2^(ex_feeder - ex_mine) that
-// brings the feeder's edge value into this lane's frame (0 for the lane without a feeder).
-template <int CPL, int DIR>
-__device__ __forceinline__ float renorm(float (&v)[CPL], int& ex, int lane) {
-    float mx = v[0];
-#pragma unroll
-    for (int i = 1; i < CPL; ++i) mx = fmaxf(mx, v[i]);
-    const int own = mx > 0.0f ? ex + ilogb_pos(mx) - kTarget : kNoMass;
-    const float edge = DIR > 0 ? v[CPL - 1] : v[0];
-    const int amag = edge > 0.0f ? ex + ilogb_pos(edge) : kNoMass;
-    int nb = DIR > 0 ? __shfl_up_sync(kFull, amag, 1) : __shfl_down_sync(kFull, amag, 1);
-    if ((DIR > 0 && lane == 0) || (DIR < 0 && lane == 31)) nb = kNoMass;
-    int nw = max(own, nb - kTarget - kSlack);
-    if (nw <= kNoMass / 2) nw = ex;  // nothing here and nothing arriving: keep the frame
-    const int shift = ex - nw;
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) v[i] = scale_pow2(v[i], shift);
-    ex = nw;
-    const int fe = DIR > 0 ? __shfl_up_sync(kFull, ex, 1) : __shfl_down_sync(kFull, ex, 1);
-    float g = pow2i(max(-126, min(126, fe - ex)));
-    if ((DIR > 0 && lane == 0) || (DIR < 0 && lane == 31)) g = 0.0f;
-    return g;
-}
-
 // Conversion of NR consecutive (in sweep order) rows of a stage from log-probabilities to
 // probabilities, in place, with the length masks: tokens >= U have e = s = 0, the last token and
 // the last frame cannot shift.  All loads first, then the EX2s, then the stores (ILP across rows).
@@ -160,122 +136,240 @@ __device__ __forceinline__ void prep_rows(float* e0, float* s0, const int in_str
     }
 }
 
-// NR consecutive rows of the recursion: the rows' probabilities are pulled into registers first
-// (all shared-memory latencies overlap), then the rows run as straight-line code.  The state
-// BEFORE each step is written out (scratch row in phase 1, shared state row in phase 2).
-// RANK 0: alpha'(u) = alpha(u) e(u) + alpha(u-1) s(u-1);  RANK 1: beta'(u) = e(u) beta(u) + s(u) beta(u+1).
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
-// H1 / H2 are called after the rows with local index D1 / D2 (-1: never): the recursion warp hangs
-// the two halves of its re-normalisation decision there, so their shuffles overlap the last rows.
-// FULL: max_u == 32*CPL, the common case (U = 32, 64, 128, 256): every stride is a compile-time
-// constant, so the loads and stores use immediate offsets and need no bounds predicates.
-template <int CPL, int RANK, bool TO_SMEM, int NR, bool FULL, int D1 = -1, int D2 = -1, typename H1 = NoHook,
-          typename H2 = NoHook>
-__device__ __forceinline__ void chain_rows(float (&v)[CPL], const float g, const float* e0, const float* s0,
-                                           int in_stride, float* st0, long long st_stride, const int ex, int UP,
-                                           const int lane, const int c0, int max_u, H1 h1 = NoHook(),
-                                           H2 h2 = NoHook()) {
-    if (FULL) {
-        max_u = 32 * CPL;
-        UP = 32 * CPL;
-        in_stride = RANK == 0 ? 32 * CPL : -32 * CPL;
-        st_stride = TO_SMEM ? 32 * CPL : (RANK == 0 ? 32 * CPL + 32 : -(32 * CPL + 32));
-    }
-    float E[NR][CPL], S[NR][CPL];
+
+// ---- skewed recursion -----------------------------------------------------------------------------
+// A warp issues in order, so a row written as "shuffle the edge cell, then use it" stalls for the
+// whole shuffle latency every row (measured: 52 cycles/row for 14 instructions).  Here the cell
+// that CONSUMES the neighbour lane's value lags one row behind the lane's other cells and uses a
+// shuffle that was issued two rows earlier, so nothing waits:
+//   RANK 0 (alpha): a[0] = alpha(c0)[s-1], a[i>=1] = alpha(c0+i)[s] before the step of row s;
+//   RANK 1 (beta):  a[CPL-1] lags, the others lead (mirror image, sweep order instead of t).
+// Step s: lag cell  <- lag*Ec + inA*Qc     (Ec, Qc: its emit prob / feeding shift prob x frame factor
+//                                          of the PREVIOUS row, carried in registers)
+//         row s of the state is now complete and is written out,
+//         the other cells advance to row s+1, the new edge cell is shuffled (→ inB, used at s+2).
+template <int CPL>
+struct ChainState {
+    float a[CPL];
+    float inA, inB;  // pending shuffle results: raw neighbour values in the NEIGHBOUR's frame
+    float Ec, Pc;    // carry of the lag cell: emit probability and feeding shift probability
+    __device__ __forceinline__ void init(int rank, int lane, int U) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        load_cells<CPL>(e0 + r * in_stride, c0, max_u, 0.0f, E[r]);
-        load_cells<CPL>(s0 + r * in_stride, c0, max_u, 0.0f, S[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        float* dst = st0 + (long long)r * st_stride;
-        store_cells<CPL>(dst, c0, max_u, v);
-        if (!TO_SMEM) reinterpret_cast<int*>(dst)[UP + lane] = ex;
-        if (RANK == 0) {
-            float bsh[CPL];
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) bsh[i] = v[i] * S[r][i];
-            const float in = __shfl_up_sync(kFull, bsh[CPL - 1], 1);
-#pragma unroll
-            for (int i = CPL - 1; i >= 1; --i) v[i] = fmaf(v[i], E[r][i], bsh[i - 1]);
-            v[0] = fmaf(in, g, v[0] * E[r][0]);
+        for (int i = 0; i < CPL; ++i) a[i] = 0.0f;
+        if (rank == 0) {
+            if (lane == 0) a[0] = 1.0f;  // alpha(0,0) = 1
         } else {
-            const float in = __shfl_down_sync(kFull, v[0], 1) * g;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const float nb = (i + 1 < CPL) ? v[i + 1] : in;
-                v[i] = fmaf(E[r][i], v[i], S[r][i] * nb);
-            }
+            for (int i = 0; i < CPL; ++i)
+                if (lane * CPL + i == U - 1) a[i] = 1.0f;  // virtual terminal row beta(T, U-1) = 1
         }
-        if (r == D1) h1();
-        if (r == D2) h2();
+        // the state is one complete row: the next step must not advance the lag cell (identity
+        // carry), and the step after it needs the feeder's edge cell of THIS row
+        inA = 0.0f;
+        inB = rank == 0 ? __shfl_up_sync(kFull, a[CPL - 1], 1) : __shfl_down_sync(kFull, a[0], 1);
+        Ec = 1.0f; Pc = 0.0f;
+    }
+    // Brings the lag cell up to the row of the others (the state becomes one complete row) and
+    // arms the identity carry so the next step does not advance it twice.
+    __device__ __forceinline__ void flush(int rank, float g) {
+        constexpr int L = CPL - 1;
+        if (rank == 0) a[0] = fmaf(inA, Pc * g, a[0] * Ec);
+        else a[L] = fmaf(inA, Pc * g, a[L] * Ec);
+        Ec = 1.0f; Pc = 0.0f;
+    }
+};
+
+// One step.  E,S: this lane's probabilities of row s; P: alpha only, s(row s, c0-1).
+// out = the complete state row s (what the old code stored "before the step").
+template <int CPL, int RANK>
+__device__ __forceinline__ void skew_step(ChainState<CPL>& cs, const float (&E)[CPL], const float (&S)[CPL],
+                                          const float P, const float g, float (&out)[CPL]) {
+    static_assert(CPL >= 2, "the skewed recursion needs two cells per lane");
+    constexpr int L = CPL - 1;
+    const float Qc = cs.Pc * g;
+    if (RANK == 0) {
+        float last_new;
+        if (CPL > 2) last_new = fmaf(cs.a[L], E[L], cs.a[L - 1] * S[L - 1]);
+        const float a0n = fmaf(cs.a[0], cs.Ec, cs.inA * Qc);
+        out[0] = a0n;
+#pragma unroll
+        for (int i = 1; i < CPL; ++i) out[i] = cs.a[i];
+        if (CPL == 2) last_new = fmaf(cs.a[1], E[1], a0n * S[0]);
+        const float sh = __shfl_up_sync(kFull, last_new, 1);
+#pragma unroll
+        for (int i = L - 1; i >= 2; --i) cs.a[i] = fmaf(cs.a[i], E[i], cs.a[i - 1] * S[i - 1]);
+        if (CPL > 2) cs.a[1] = fmaf(cs.a[1], E[1], a0n * S[0]);
+        cs.a[L] = last_new;
+        cs.a[0] = a0n;
+        cs.inA = cs.inB;
+        cs.inB = sh;
+        cs.Ec = E[0];
+        cs.Pc = P;
+    } else {
+        float first_new;
+        if (CPL > 2) first_new = fmaf(E[0], cs.a[0], S[0] * cs.a[1]);
+        const float aLn = fmaf(cs.a[L], cs.Ec, cs.inA * Qc);
+        out[L] = aLn;
+#pragma unroll
+        for (int i = 0; i < L; ++i) out[i] = cs.a[i];
+        if (CPL == 2) first_new = fmaf(E[0], cs.a[0], S[0] * aLn);
+        const float sh = __shfl_down_sync(kFull, first_new, 1);
+#pragma unroll
+        for (int i = 1; i < L - 1; ++i) cs.a[i] = fmaf(E[i], cs.a[i], S[i] * cs.a[i + 1]);
+        if (CPL > 2) cs.a[L - 1] = fmaf(E[L - 1], cs.a[L - 1], S[L - 1] * aLn);
+        cs.a[0] = first_new;
+        cs.a[L] = aLn;
+        cs.inA = cs.inB;
+        cs.inB = sh;
+        cs.Ec = E[L];
+        cs.Pc = S[L];
     }
 }
 
-// One full stage (8 rows) with the row loads software-pipelined: the probabilities of chunk c+1 are
-// requested before chunk c is computed, so shared-memory latency (and queueing behind the helper
-// warps' traffic) overlaps the arithmetic.  Hooks: d1 after row 5, d2 after row 6.
-template <int CPL, int RANK, bool TO_SMEM, bool FULL, int DBG, typename H1, typename H2>
-__device__ __forceinline__ void chain_stage(float (&v)[CPL], const float g, const float* e0, const float* s0,
-                                            int in_stride, float* st0, long long st_stride, const int ex, int UP,
-                                            const int lane, const int c0, int max_u, H1 h1, H2 h2) {
-    if (FULL) {
-        max_u = 32 * CPL;
-        UP = 32 * CPL;
-        in_stride = RANK == 0 ? 32 * CPL : -32 * CPL;
-        st_stride = TO_SMEM ? 32 * CPL : (RANK == 0 ? 32 * CPL + 32 : -(32 * CPL + 32));
-    }
-    constexpr int NR = CPL <= 4 ? 4 : 2;  // rows per chunk (register budget)
-    constexpr int NC = kG / NR;
-    float E[2][NR][CPL], S[2][NR][CPL];
+// NR rows (one or two full stages, max_u == 32*CPL) as straight-line code.  The rows' probabilities
+// are pulled into registers a chunk ahead.  e0/s0: first row IN SWEEP ORDER of the stage (rank 1 walks
+// memory backwards); rows [8, 16) of a 16-row round come from e1/s1.  State rows go to st0 + q*stride
+// (shared, stride max_u) or to the global scratch (stride +-SU, lane exponents behind the row).
+// Hooks: h1 after row NR-3, h2 after row NR-2 (the two halves of the re-normalisation decision).
+template <int CPL, int RANK, bool TO_SMEM, int NR, typename H1, typename H2>
+__device__ __forceinline__ void chain_round_skew(ChainState<CPL>& cs, const float g, const float* e0, const float* s0,
+                                                 float* st0, const int ex, const int lane, H1 h1, H2 h2,
+                                                 const float* e1 = nullptr, const float* s1 = nullptr,
+                                                 float* st1 = nullptr) {
+    constexpr int max_u = 32 * CPL, SU = max_u + 32;
+    constexpr int istr = RANK == 0 ? max_u : -max_u;
+    constexpr int sstr = TO_SMEM ? max_u : (RANK == 0 ? SU : -SU);
+    constexpr int CH = CPL <= 4 ? 4 : 2;  // rows per chunk (register budget)
+    constexpr int NC = NR / CH;
+    const int c0 = lane * CPL;
+    const int pc = c0 > 0 ? c0 - 1 : 0;
+    float E[2][CH][CPL], S[2][CH][CPL], P[2][CH];
+    auto load_chunk = [&](int c, int buf) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        if (DBG & 2) {
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) { E[0][r][i] = 0.6f + 1e-3f * lane; S[0][r][i] = 0.4f; E[1][r][i] = 0.6f; S[1][r][i] = 0.4f + 1e-3f * lane; }
-        } else {
-            load_cells<CPL>(e0 + r * in_stride, c0, max_u, 0.0f, E[0][r]);
-            load_cells<CPL>(s0 + r * in_stride, c0, max_u, 0.0f, S[0][r]);
+        for (int r = 0; r < CH; ++r) {
+            const int q = c * CH + r;
+            const float* er = (q < 8 ? e0 : e1) + (q & 7) * istr;
+            const float* sr = (q < 8 ? s0 : s1) + (q & 7) * istr;
+            load_cells<CPL>(er, c0, max_u, 0.0f, E[buf][r]);
+            load_cells<CPL>(sr, c0, max_u, 0.0f, S[buf][r]);
+            if (RANK == 0) P[buf][r] = sr[pc];
+            else P[buf][r] = 0.0f;
         }
-    }
+    };
+    load_chunk(0, 0);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
-        if (c + 1 < NC && !(DBG & 2)) {
+        if (c + 1 < NC) load_chunk(c + 1, (c + 1) & 1);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                load_cells<CPL>(e0 + ((c + 1) * NR + r) * in_stride, c0, max_u, 0.0f, E[(c + 1) & 1][r]);
-                load_cells<CPL>(s0 + ((c + 1) * NR + r) * in_stride, c0, max_u, 0.0f, S[(c + 1) & 1][r]);
-            }
+        for (int r = 0; r < CH; ++r) {
+            const int q = c * CH + r;
+            float out[CPL];
+            skew_step<CPL, RANK>(cs, E[c & 1][r], S[c & 1][r], P[c & 1][r], g, out);
+            float* dst = (q < 8 ? st0 : st1) + (q & 7) * sstr;
+            store_cells<CPL>(dst, c0, max_u, out);
+            if (!TO_SMEM) reinterpret_cast<int*>(dst)[max_u + lane] = ex;
+            if (q == NR - 3) h1();
+            if (q == NR - 2) h2();
         }
+    }
+}
+
+// Non-blocking probe of an mbarrier phase (the chain warp probes the NEXT round's barriers while it
+// computes the current one, so a hand-off that is already complete costs no round trip).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Gradients of NRP consecutive (sweep order) rows of one stage, all loads first (ILP across rows).
+// Row q of the stage: E,S probabilities, the chain's state row (own sweep) and the partner's
+// scratch row x (other sweep).  gamma = alpha * p * beta / Z with the exponents split over two
+// power-of-two factors.
+struct PostCtx {
+    float* sp;        // ring slot
+    int off_e, off_s, off_x, off_v;
+    int max_u, SU, UP;
+    int dir, rank, lane, c0;
+    int cnt;          // rows in the stage
+    int t_base;       // frame of the stage's row 0 (sweep order)
+    int T, U;
+    int ex_state;     // this lane's exponent of the chain's state rows
+    int f_M;          // likelihood: Z = sum * 2^M
+    float f_inv_sum;
+    bool f_dead;
+    float* ge;
+    float* gs;
+    unsigned* status;
+};
+
+template <int CPL, int NRP>
+__device__ __forceinline__ void post_rows(const PostCtx& c, const int q0) {
+    float E[NRP][CPL], S[NRP][CPL], VA[NRP][CPL], VB[NRP][CPL];
+    int exA[NRP], exB[NRP];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int q = c * NR + r;
-            float* dst = st0 + (long long)q * st_stride;
-            if (!(DBG & 1)) {
-                store_cells<CPL>(dst, c0, max_u, v);
-                if (!TO_SMEM) reinterpret_cast<int*>(dst)[UP + lane] = ex;
+    for (int r = 0; r < NRP; ++r) {
+        const int q = q0 + r;
+        const int idx = c.dir > 0 ? q : c.cnt - 1 - q;
+        load_cells<CPL>(c.sp + c.off_e + idx * c.max_u, c.c0, c.max_u, 0.0f, E[r]);
+        load_cells<CPL>(c.sp + c.off_s + idx * c.max_u, c.c0, c.max_u, 0.0f, S[r]);
+        const float* xrow = c.sp + c.off_x + idx * c.SU;
+        const int ex_x = reinterpret_cast<const int*>(xrow)[c.UP + c.lane];
+        if (c.rank == 0) {
+            load_cells<CPL>(c.sp + c.off_v + q * c.max_u, c.c0, c.max_u, 0.0f, VA[r]);
+            load_cells<CPL>(xrow, c.c0, c.max_u, 0.0f, VB[r]);
+            exA[r] = c.ex_state; exB[r] = ex_x;
+        } else {
+            load_cells<CPL>(xrow, c.c0, c.max_u, 0.0f, VA[r]);
+            load_cells<CPL>(c.sp + c.off_v + q * c.max_u, c.c0, c.max_u, 0.0f, VB[r]);
+            exA[r] = ex_x; exB[r] = c.ex_state;
+        }
+    }
+    float edge[NRP];
+    int exBn[NRP];
+#pragma unroll
+    for (int r = 0; r < NRP; ++r) {
+        exBn[r] = __shfl_down_sync(kFull, exB[r], 1);
+        edge[r] = __shfl_down_sync(kFull, VB[r][0], 1);
+    }
+#pragma unroll
+    for (int r = 0; r < NRP; ++r) {
+        const int t = c.t_base + c.dir * (q0 + r);
+        // beta(t+1, u+1): in-lane neighbour, or lane+1's first cell re-framed
+        float vbn_edge = scale_pow2(edge[r], exBn[r] - exB[r]);
+        if (c.lane == 31) vbn_edge = 0.0f;
+        const int kf = max(-252, min(252, exA[r] + exB[r] - c.f_M));
+        const int k1 = kf >> 1;
+        const float fa = pow2i(max(-126, k1));
+        const float fb = pow2i(max(-126, kf - k1)) * c.f_inv_sum;
+        float g1[CPL], g2[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const float nb = (i + 1 < CPL) ? VB[r][i + 1] : vbn_edge;
+            const float va = VA[r][i] * fa;
+            g1[i] = c.f_dead ? 0.0f : va * ((E[r][i] * VB[r][i]) * fb);
+            g2[i] = c.f_dead ? 0.0f : va * ((S[r][i] * nb) * fb);
+        }
+        store_cells_cs<CPL>(c.ge + (size_t)t * c.max_u, c.c0, c.max_u, g1);
+        store_cells_cs<CPL>(c.gs + (size_t)t * c.max_u, c.c0, c.max_u, g2);
+        // consistency: occupancy of the terminal cell (alpha side) / of frame 0 (beta side) must
+        // be 1 — these are independent likelihood estimates.
+        if (!c.f_dead && (t == c.T - 1 || t == 0)) {
+            bool bad = false;
+            if (c.rank == 0 && t == c.T - 1) {
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+                    if (c.c0 + i == c.U - 1) bad = !(fabsf(g1[i] - 1.0f) < kBfConsistency);
             }
-            if (RANK == 0) {
-                float bsh[CPL];
-#pragma unroll
-                for (int i = 0; i < CPL; ++i) bsh[i] = v[i] * S[c & 1][r][i];
-                const float in = __shfl_up_sync(kFull, bsh[CPL - 1], 1);
-#pragma unroll
-                for (int i = CPL - 1; i >= 1; --i) v[i] = fmaf(v[i], E[c & 1][r][i], bsh[i - 1]);
-                v[0] = fmaf(in, g, v[0] * E[c & 1][r][0]);
-            } else {
-                const float in = __shfl_down_sync(kFull, v[0], 1) * g;
-#pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    const float nb = (i + 1 < CPL) ? v[i + 1] : in;
-                    v[i] = fmaf(E[c & 1][r][i], v[i], S[c & 1][r][i] * nb);
-                }
-            }
-            if (q == 5) h1();
-            if (q == 6) h2();
+            if (c.rank == 1 && t == 0 && c.lane == 0) bad = !(fabsf(g1[0] + g2[0] - 1.0f) < kBfConsistency);
+            if (bad) atomicOr(c.status, (unsigned)kBfInconsistent);
         }
     }
 }
@@ -342,7 +436,6 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
     long long st_wait[4] = {0, 0, 0, 0};
     const long long st_t0 = p.stats ? clock64() : 0;
     long long st_sync = 0, st_phase0 = 0, st_prep = 0, st_post = 0;
-    long long st_min = 1 << 30, st_max = 0, st_n = 0, st_lt400 = 0, st_lt800 = 0;  // chain: per-stage row time histogram
     auto timed_cluster_sync = [&]() {
         if (p.stats) {
             const long long t0 = clock64();
@@ -447,45 +540,39 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
         }
     } else if (warp == 0) {
         // ------------------------------- chain -------------------------------
-        float v[CPL];
-        int ex = 0;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) v[i] = 0.0f;
-        if (rank == 0) {
-            if (lane == 0) v[0] = 1.0f;  // alpha(0,0) = 1
-        } else {
-#pragma unroll
-            for (int i = 0; i < CPL; ++i)
-                if (c0 + i == U - 1) v[i] = 1.0f;  // virtual terminal row beta(T, U-1) = 1
-        }
+        ChainState<CPL> cs;
+        cs.init((int)rank, lane, U);
+        int ex = 0;     // this lane's frame (shared exponent of its CPL cells)
+        int nb_ex = 0;  // the feeding lane's frame
         const bool edge_lane = rank == 0 ? lane == 0 : lane == 31;  // the lane without a feeder
         const bool full_u = max_u == 32 * CPL;
-        float g = edge_lane ? 0.0f : 1.0f;  // 2^(ex_feeder - ex_mine); all frames start at 0
-        // Pipelined re-normalisation: the new frame of stage k+1 is DECIDED during stage k (two
-        // shuffles whose results are not needed before the next stage) and APPLIED at the start of
-        // stage k+1, so no shuffle latency sits between the rows.
+        float g = edge_lane ? 0.0f : 1.0f;  // 2^(nb_ex - ex); all frames start at 0
+        // Pipelined re-normalisation: the new frame of round k+1 is DECIDED during round k (two
+        // shuffles whose results are not needed before the next round) and APPLIED at the start of
+        // round k+1, so no shuffle latency sits between the rows.
         bool have_dec = false;
         int ex_dec = 0, nbex_dec = 0;
-        auto store_scratch = [&](int row) {
-            float* r = scr + (size_t)row * SU;
-            store_cells<CPL>(r, c0, max_u, v);
-            reinterpret_cast<int*>(r)[UP + lane] = ex;
-        };
         auto apply_decision = [&]() {
             if (!have_dec) return;
             const int shift = ex - ex_dec;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) v[i] = scale_pow2(v[i], shift);
+            for (int i = 0; i < CPL; ++i) cs.a[i] = scale_pow2(cs.a[i], shift);
+            // pending neighbour values follow the neighbour's re-framing
+            const int fshift = nb_ex - nbex_dec;
+            cs.inA = scale_pow2(cs.inA, fshift);
+            cs.inB = scale_pow2(cs.inB, fshift);
             ex = ex_dec;
-            g = edge_lane ? 0.0f : pow2i(max(-126, min(126, nbex_dec - ex_dec)));
+            nb_ex = nbex_dec;
+            g = edge_lane ? 0.0f : pow2i(max(-126, min(126, nb_ex - ex)));
+            have_dec = false;
         };
         // decision, part 1: magnitudes of this lane and (shuffle in flight) of the feeder's edge cell
         auto decide_1 = [&](int& own, int& nbmag) {
-            float mx = v[0];
+            float mx = cs.a[0];
 #pragma unroll
-            for (int i = 1; i < CPL; ++i) mx = fmaxf(mx, v[i]);
+            for (int i = 1; i < CPL; ++i) mx = fmaxf(mx, cs.a[i]);
             own = mx > 0.0f ? ex + ilogb_pos(mx) - kTarget : kNoMass;
-            const float edge = rank == 0 ? v[CPL - 1] : v[0];
+            const float edge = rank == 0 ? cs.a[CPL - 1] : cs.a[0];
             const int amag = edge > 0.0f ? ex + ilogb_pos(edge) : kNoMass;
             nbmag = rank == 0 ? __shfl_up_sync(kFull, amag, 1) : __shfl_down_sync(kFull, amag, 1);
         };
@@ -501,8 +588,11 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
         unsigned kg = 0;
         for (int phase = 0; phase < 2; ++phase) {
             if (phase == 1) {
-                // hand the last phase-1 state over, then meet the partner
-                store_scratch(rank == 0 ? m - 1 : m);
+                // complete the last phase-1 row, hand it over, then meet the partner
+                cs.flush((int)rank, g);
+                float* r = scr + (size_t)(rank == 0 ? m - 1 : m) * SU;
+                store_cells<CPL>(r, c0, max_u, cs.a);
+                reinterpret_cast<int*>(r)[UP + lane] = ex;
                 __threadfence();
                 fence_proxy_async();
                 timed_cluster_sync();
@@ -510,152 +600,111 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
             const int Pn = ph[phase].n, Pt0 = ph[phase].t0, Pnst = ph[phase].nst;
             int slot = (int)(kg % (unsigned)NS);
             unsigned par = (kg / (unsigned)NS) & 1u;
-            for (int k = 0; k < Pnst; ++k) {
-                // Fast path: two full stages (16 rows) per barrier round trip.  Waits, frame update and
-                // hand-off cost ~350 cycles per round, so amortising them over 16 rows instead of 8
-                // matters more than anything else in this warp.
-                if (full_u && k + 1 < Pnst && Pn - (k + 1) * kG >= kG) {
-                    const int slot2 = slot + 1 == NS ? 0 : slot + 1;
-                    const unsigned par2 = slot + 1 == NS ? par ^ 1u : par;
-                    tl_mark(0, (int)kg + k, 0);
-                    timed_wait(1, smem_u32(prep_full + slot), par);
-                    timed_wait(1, smem_u32(prep_full + slot2), par2);
-                    tl_mark(0, (int)kg + k, 1);
-                    float* spA = ring + (size_t)slot * stage_floats;
-                    float* spB = ring + (size_t)slot2 * stage_floats;
-                    const int j0 = k * kG;
-                    const long long tr0 = p.stats ? clock64() : 0;
-                    apply_decision();
-                    if (phase == 1) {
-                        reinterpret_cast<int*>(spA + off_ve)[lane] = ex;
-                        reinterpret_cast<int*>(spB + off_ve)[lane] = ex;
-                    }
-                    int own = kNoMass, nbmag = kNoMass;
-                    auto d1 = [&]() { decide_1(own, nbmag); };
-                    auto d2 = [&]() { decide_2(own, nbmag); };
-                    const long long tr1 = p.stats ? clock64() : 0;
-                    st_post += tr1 - tr0;
-                    const int eo = dir > 0 ? 0 : (kG - 1) * max_u;
-                    const int istr = dir * max_u;
-                    float* st_gA = scr + (size_t)(Pt0 + dir * j0 + (rank == 0 ? 0 : 1)) * SU;
-                    float* st_gB = st_gA + (long long)dir * kG * SU;
-                    const long long sstr_g = (long long)dir * SU, sstr_s = (long long)max_u;
-                    if (rank == 0) {
-                        if (phase == 0) {
-                            chain_stage<CPL, 0, false, true, 0>(v, g, spA + off_e + eo, spA + off_s + eo, istr, st_gA, sstr_g, ex, UP, lane, c0, max_u, NoHook(), NoHook());
-                            chain_stage<CPL, 0, false, true, 0>(v, g, spB + off_e + eo, spB + off_s + eo, istr, st_gB, sstr_g, ex, UP, lane, c0, max_u, d1, d2);
-                        } else {
-                            chain_stage<CPL, 0, true, true, 0>(v, g, spA + off_e + eo, spA + off_s + eo, istr, spA + off_v, sstr_s, ex, UP, lane, c0, max_u, NoHook(), NoHook());
-                            chain_stage<CPL, 0, true, true, 0>(v, g, spB + off_e + eo, spB + off_s + eo, istr, spB + off_v, sstr_s, ex, UP, lane, c0, max_u, d1, d2);
-                        }
-                    } else {
-                        if (phase == 0) {
-                            chain_stage<CPL, 1, false, true, 0>(v, g, spA + off_e + eo, spA + off_s + eo, istr, st_gA, sstr_g, ex, UP, lane, c0, max_u, NoHook(), NoHook());
-                            chain_stage<CPL, 1, false, true, 0>(v, g, spB + off_e + eo, spB + off_s + eo, istr, st_gB, sstr_g, ex, UP, lane, c0, max_u, d1, d2);
-                        } else {
-                            chain_stage<CPL, 1, true, true, 0>(v, g, spA + off_e + eo, spA + off_s + eo, istr, spA + off_v, sstr_s, ex, UP, lane, c0, max_u, NoHook(), NoHook());
-                            chain_stage<CPL, 1, true, true, 0>(v, g, spB + off_e + eo, spB + off_s + eo, istr, spB + off_v, sstr_s, ex, UP, lane, c0, max_u, d1, d2);
-                        }
-                    }
-                    if (p.stats) {
-                        const long long dt = clock64() - tr1;
-                        st_prep += dt;
-                        st_min = min(st_min, dt); st_max = max(st_max, dt); st_n += 2;
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (phase == 0) {
-                            mbar_arrive_relaxed_n(smem_u32(state_full + slot), 1);
-                            mbar_arrive_relaxed_n(smem_u32(slot_free + slot), 2);
-                            mbar_arrive_relaxed_n(smem_u32(state_full + slot2), 1);
-                            mbar_arrive_relaxed_n(smem_u32(slot_free + slot2), 2);
-                        } else {
-                            mbar_arrive(smem_u32(state_full + slot));
-                            mbar_arrive(smem_u32(state_full + slot2));
-                        }
-                    }
-                    tl_mark(0, (int)kg + k, 2);
-                    tl_mark(0, (int)kg + k + 1, 2);
-                    ++k;
-                    for (int z = 0; z < 2; ++z)
-                        if (++slot == NS) { slot = 0; par ^= 1u; }
-                    continue;
-                }
+            bool pre0 = false, pre1 = false;  // prefetched state of the next round's barriers
+            for (int k = 0; k < Pnst;) {
+                const bool two = full_u && Pn - k * kG >= 2 * kG && !(p.debug_skip & 2);  // fast path: two full stages per round
+                const int slot2 = slot + 1 == NS ? 0 : slot + 1;
+                const unsigned par2 = slot + 1 == NS ? par ^ 1u : par;
                 tl_mark(0, (int)kg + k, 0);
-                timed_wait(1, smem_u32(prep_full + slot), par);
+                {
+                    const long long t0 = p.stats ? clock64() : 0;
+                    if (!__all_sync(kFull, pre0)) mbar_wait_warp(smem_u32(prep_full + slot), par);
+                    if (two && !__all_sync(kFull, pre1)) mbar_wait_warp(smem_u32(prep_full + slot2), par2);
+                    if (p.stats) st_wait[1] += clock64() - t0;
+                }
                 tl_mark(0, (int)kg + k, 1);
-                float* sp = ring + (size_t)slot * stage_floats;
+                const int adv = two ? 2 : 1;
+                // probe the barriers of the next round now; the answer is consumed a round later
+                {
+                    int s3 = slot, q3 = (int)par;
+                    for (int z = 0; z < adv; ++z)
+                        if (++s3 == NS) { s3 = 0; q3 ^= 1; }
+                    const int s4 = s3 + 1 == NS ? 0 : s3 + 1;
+                    const int q4 = s3 + 1 == NS ? q3 ^ 1 : q3;
+                    pre0 = !(p.debug_skip & 1) && k + adv < Pnst && mbar_test(smem_u32(prep_full + s3), (uint32_t)q3);
+                    pre1 = !(p.debug_skip & 1) && k + adv + 1 < Pnst && mbar_test(smem_u32(prep_full + s4), (uint32_t)q4);
+                }
+                float* spA = slot_ptr(slot);
+                float* spB = slot_ptr(slot2);
                 const int j0 = k * kG;
                 const int cnt = min(kG, Pn - j0);
                 const long long tr0 = p.stats ? clock64() : 0;
                 apply_decision();
-                if (phase == 1) reinterpret_cast<int*>(sp + off_ve)[lane] = ex;
+                if (phase == 1) {
+                    reinterpret_cast<int*>(spA + off_ve)[lane] = ex;
+                    if (two) reinterpret_cast<int*>(spB + off_ve)[lane] = ex;
+                }
                 int own = kNoMass, nbmag = kNoMass;
                 auto d1 = [&]() { decide_1(own, nbmag); };
                 auto d2 = [&]() { decide_2(own, nbmag); };
-                const long long tr1 = p.stats ? clock64() : 0;
-                st_post += tr1 - tr0;  // chain warp: cycles in renorm
-                if (p.stats) st_lt400 = min((long long)__popc(__activemask()), st_n == 0 ? 32LL : st_lt400);  // divergence probe
-                if (cnt == kG) {
-                    const float* e0 = sp + off_e + (dir > 0 ? 0 : (kG - 1) * max_u);
-                    const float* s0 = sp + off_s + (dir > 0 ? 0 : (kG - 1) * max_u);
-                    const int istr = dir * max_u;
-                    // decision from the state after row 5 (part 1) / row 6 (part 2): 2 rows stale when applied.
-                    // phase 1 state rows go to scratch (alpha(t) → row t, beta(t+1) → row t+1), phase 2 to shared.
-                    float* st_g = scr + (size_t)(Pt0 + dir * j0 + (rank == 0 ? 0 : 1)) * SU;  // global scratch
-                    float* st_s = sp + off_v;                                                   // shared state rows
-                    const long long sstr_g = (long long)dir * SU, sstr_s = (long long)max_u;
-#define SSNT_STAGE_G(RANK_, FULL_) chain_stage<CPL, RANK_, false, FULL_, 0>(v, g, e0, s0, istr, st_g, sstr_g, ex, UP, lane, c0, max_u, d1, d2)
-#define SSNT_STAGE_S(RANK_, FULL_) chain_stage<CPL, RANK_, true, FULL_, 0>(v, g, e0, s0, istr, st_s, sstr_s, ex, UP, lane, c0, max_u, d1, d2)
-#ifdef SSNT_BF_DEBUG_VARIANTS
-                    const int dbg = (p.debug_skip >> 2) & 3;
-                    if (dbg == 1) { if (phase == 0) chain_stage<CPL, 0, false, true, 1>(v, g, e0, s0, istr, st_g, sstr_g, ex, UP, lane, c0, max_u, d1, d2); else chain_stage<CPL, 0, true, true, 1>(v, g, e0, s0, istr, st_s, sstr_s, ex, UP, lane, c0, max_u, d1, d2); }
-                    else if (dbg == 2) { if (phase == 0) chain_stage<CPL, 0, false, true, 2>(v, g, e0, s0, istr, st_g, sstr_g, ex, UP, lane, c0, max_u, d1, d2); else chain_stage<CPL, 0, true, true, 2>(v, g, e0, s0, istr, st_s, sstr_s, ex, UP, lane, c0, max_u, d1, d2); }
-                    else if (dbg == 3) { if (phase == 0) chain_stage<CPL, 0, false, true, 3>(v, g, e0, s0, istr, st_g, sstr_g, ex, UP, lane, c0, max_u, d1, d2); else chain_stage<CPL, 0, true, true, 3>(v, g, e0, s0, istr, st_s, sstr_s, ex, UP, lane, c0, max_u, d1, d2); }
-                    else
-#endif
-                    if (full_u) {
-                        if (rank == 0) { if (phase == 0) SSNT_STAGE_G(0, true); else SSNT_STAGE_S(0, true); }
-                        else           { if (phase == 0) SSNT_STAGE_G(1, true); else SSNT_STAGE_S(1, true); }
-                    } else {
-                        if (rank == 0) { if (phase == 0) SSNT_STAGE_G(0, false); else SSNT_STAGE_S(0, false); }
-                        else           { if (phase == 0) SSNT_STAGE_G(1, false); else SSNT_STAGE_S(1, false); }
-                    }
-#undef SSNT_STAGE_G
-#undef SSNT_STAGE_S
-                } else {
-                    for (int q = 0; q < cnt; ++q) {
-                        const int t = Pt0 + dir * (j0 + q);
-                        const int idx = dir > 0 ? q : cnt - 1 - q;
-                        float* st0 = phase == 0 ? scr + (size_t)(rank == 0 ? t : t + 1) * SU : sp + off_v + q * max_u;
+                // first row of the stage in sweep order; state rows: phase 1 → global scratch
+                // (alpha(t) → row t, beta(t+1) → row t+1), phase 2 → the slot's shared state rows.
+                const int eo = dir > 0 ? 0 : (kG - 1) * max_u;
+                float* st_g = scr + (size_t)(Pt0 + dir * j0 + (rank == 0 ? 0 : 1)) * SU;
+                if (full_u && cnt == kG && !(p.debug_skip & 8)) {
+                    const float* eA = spA + off_e + eo;
+                    const float* sA = spA + off_s + eo;
+                    const float* eB = spB + off_e + eo;
+                    const float* sB = spB + off_s + eo;
+                    float* st_g2 = st_g + (long long)dir * kG * SU;
+                    if (two) {
                         if (rank == 0) {
-                            if (phase == 0) chain_rows<CPL, 0, false, 1, false>(v, g, sp + off_e + idx * max_u, sp + off_s + idx * max_u, 0, st0, 0, ex, UP, lane, c0, max_u);
-                            else chain_rows<CPL, 0, true, 1, false>(v, g, sp + off_e + idx * max_u, sp + off_s + idx * max_u, 0, st0, 0, ex, UP, lane, c0, max_u);
+                            if (phase == 0) chain_round_skew<CPL, 0, false, 16>(cs, g, eA, sA, st_g, ex, lane, d1, d2, eB, sB, st_g2);
+                            else chain_round_skew<CPL, 0, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
                         } else {
-                            if (phase == 0) chain_rows<CPL, 1, false, 1, false>(v, g, sp + off_e + idx * max_u, sp + off_s + idx * max_u, 0, st0, 0, ex, UP, lane, c0, max_u);
-                            else chain_rows<CPL, 1, true, 1, false>(v, g, sp + off_e + idx * max_u, sp + off_s + idx * max_u, 0, st0, 0, ex, UP, lane, c0, max_u);
+                            if (phase == 0) chain_round_skew<CPL, 1, false, 16>(cs, g, eA, sA, st_g, ex, lane, d1, d2, eB, sB, st_g2);
+                            else chain_round_skew<CPL, 1, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
+                        }
+                    } else {
+                        if (rank == 0) {
+                            if (phase == 0) chain_round_skew<CPL, 0, false, 8>(cs, g, eA, sA, st_g, ex, lane, d1, d2);
+                            else chain_round_skew<CPL, 0, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
+                        } else {
+                            if (phase == 0) chain_round_skew<CPL, 1, false, 8>(cs, g, eA, sA, st_g, ex, lane, d1, d2);
+                            else chain_round_skew<CPL, 1, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
                         }
                     }
-                    decide_1(own, nbmag);  // short last stage of a phase: decide from the final state
+                } else {
+                    // generic rows: short last stage of a phase, or max_u < 32*CPL
+                    const int pc = c0 > 0 ? c0 - 1 : 0;
+                    for (int q = 0; q < cnt; ++q) {
+                        const int idx = dir > 0 ? q : cnt - 1 - q;
+                        const float* er = spA + off_e + idx * max_u;
+                        const float* sr = spA + off_s + idx * max_u;
+                        float E[CPL], S[CPL], out[CPL];
+                        load_cells<CPL>(er, c0, max_u, 0.0f, E);
+                        load_cells<CPL>(sr, c0, max_u, 0.0f, S);
+                        const float P = (rank == 0 && pc < max_u) ? sr[pc] : 0.0f;
+                        if (rank == 0) skew_step<CPL, 0>(cs, E, S, P, g, out);
+                        else skew_step<CPL, 1>(cs, E, S, P, g, out);
+                        float* dst = phase == 0 ? st_g + (long long)q * dir * SU : spA + off_v + q * max_u;
+                        store_cells<CPL>(dst, c0, max_u, out);
+                        if (phase == 0) reinterpret_cast<int*>(dst)[UP + lane] = ex;
+                    }
+                    decide_1(own, nbmag);
                     decide_2(own, nbmag);
                 }
-                if (p.stats) {
-                    const long long dt = clock64() - tr1;
-                    st_prep += dt;  // chain warp: cycles in the rows
-                    if (cnt == kG) { st_min = min(st_min, dt); st_max = max(st_max, dt); ++st_n; st_lt800 += dt < 800; }
-                }
+                if (p.stats) st_prep += clock64() - tr0;
                 __syncwarp();
                 if (lane == 0) {
                     if (phase == 0) {
                         // nobody reads state rows in phase 1; the slot is free once its rows were read
                         mbar_arrive_relaxed_n(smem_u32(state_full + slot), 1);
                         mbar_arrive_relaxed_n(smem_u32(slot_free + slot), 2);
+                        if (two) {
+                            mbar_arrive_relaxed_n(smem_u32(state_full + slot2), 1);
+                            mbar_arrive_relaxed_n(smem_u32(slot_free + slot2), 2);
+                        }
                     } else {
                         mbar_arrive(smem_u32(state_full + slot));
+                        if (two) mbar_arrive(smem_u32(state_full + slot2));
                     }
                 }
                 tl_mark(0, (int)kg + k, 2);
-                if (++slot == NS) { slot = 0; par ^= 1u; }
+                if (two) tl_mark(0, (int)kg + k + 1, 2);
+                k += adv;
+                for (int z = 0; z < adv; ++z)
+                    if (++slot == NS) { slot = 0; par ^= 1u; }
             }
             kg += (unsigned)Pnst;
         }
@@ -697,8 +746,7 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                     float* e0 = sp + off_e + idx0 * max_u;
                     float* s0 = sp + off_s + idx0 * max_u;
                     const int t0r = P.t0 + dir * (j0 + q0);
-                    if (p.debug_skip & 1) {
-                    } else if (nr == kHalf) prep_rows<CPL, kHalf>(e0, s0, dir * max_u, t0r, dir, T, me, ms, c0, max_u);
+                    if (nr == kHalf) prep_rows<CPL, kHalf>(e0, s0, dir * max_u, t0r, dir, T, me, ms, c0, max_u);
                     else
                         for (int r = 0; r < nr; ++r)
                             prep_rows<CPL, 1>(e0 + r * dir * max_u, s0 + r * dir * max_u, dir * max_u, t0r + dir * r,
@@ -724,19 +772,10 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                     const int nr = max(0, min(kHalf, cnt - q0));
                     const int ex_state = reinterpret_cast<const int*>(sp + off_ve)[lane];
                     const bool ll_owner = (k == 0 && half == 0);
-                    if (!have_ll && !ll_owner) {  // wait for the log-likelihood of the meeting row
-                        named_bar_sync(1, 32 * kHelpers);
-                        f_M = __float_as_int(llinfo[0]);
-                        f_inv_sum = llinfo[1];
-                        f_dead = llinfo[2] != 0.0f;
-                        have_ll = true;
-                    }
-                    for (int r = 0; r < nr; ++r) {
-                        const int q = q0 + r;
-                        const int j = j0 + q;
-                        if ((p.debug_skip & 2) && j != 0) continue;
-                        const int t = P.t0 + dir * j;
-                        const int idx = dir > 0 ? q : cnt - 1 - q;
+                    int r_first = 0;
+                    if (ll_owner) {
+                        // log-likelihood from the meeting row j = 0: Z = sum_u alpha(m-1,u)·beta(m-1,u)
+                        const int idx = dir > 0 ? 0 : cnt - 1;
                         float E[CPL], S[CPL], VA[CPL], VB[CPL];
                         load_cells<CPL>(sp + off_e + idx * max_u, c0, max_u, 0.0f, E);
                         load_cells<CPL>(sp + off_s + idx * max_u, c0, max_u, 0.0f, S);
@@ -744,89 +783,70 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                         const int ex_x = reinterpret_cast<const int*>(xrow)[UP + lane];
                         int exA, exB;
                         if (rank == 0) {
-                            load_cells<CPL>(sp + off_v + q * max_u, c0, max_u, 0.0f, VA);
+                            load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VA);
                             load_cells<CPL>(xrow, c0, max_u, 0.0f, VB);
                             exA = ex_state; exB = ex_x;
                         } else {
                             load_cells<CPL>(xrow, c0, max_u, 0.0f, VA);
-                            load_cells<CPL>(sp + off_v + q * max_u, c0, max_u, 0.0f, VB);
+                            load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VB);
                             exA = ex_x; exB = ex_state;
                         }
-                        // beta(t+1, u+1): in-lane neighbour, or lane+1's first cell re-framed
                         const int exBn = __shfl_down_sync(kFull, exB, 1);
                         float vbn_edge = scale_pow2(__shfl_down_sync(kFull, VB[0], 1), exBn - exB);
                         if (lane == 31) vbn_edge = 0.0f;
-                        float pe[CPL], ps[CPL];  // e·beta(t+1,u), s·beta(t+1,u+1)
+                        const int EL = exA + exB;
+                        float w = 0.0f;
 #pragma unroll
                         for (int i = 0; i < CPL; ++i) {
                             const float nb = (i + 1 < CPL) ? VB[i + 1] : vbn_edge;
-                            pe[i] = E[i] * VB[i];
-                            ps[i] = S[i] * nb;
+                            w += VA[i] * (E[i] * VB[i] + S[i] * nb);
                         }
-                        const int EL = exA + exB;
-                        if (j == 0) {
-                            // log-likelihood from the meeting row: Z = sum_u alpha(m-1,u)·beta(m-1,u)
-                            float w = 0.0f;
+                        const bool finite = w == w && w < 3.0e38f;
+                        int M = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
 #pragma unroll
-                            for (int i = 0; i < CPL; ++i) w += VA[i] * (pe[i] + ps[i]);
-                            const bool finite = w == w && w < 3.0e38f;
-                            int key = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
-                            int M = key;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
-                            float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
-                            const float sum = warp_sum(part);
-                            const unsigned bad = __ballot_sync(kFull, !finite);
-                            unsigned st = 0;
-                            if (bad) st |= kBfNonFinite;
-                            if (M <= kNoMass / 2 || !(sum > 0.0f)) st |= kBfNoMass;
-                            f_M = M;
-                            f_inv_sum = st ? 0.0f : 1.0f / sum;
-                            f_dead = st != 0;
-                            have_ll = true;
-                            if (lane == 0) {
-                                llinfo[0] = __int_as_float(M);
-                                llinfo[1] = f_inv_sum;
-                                llinfo[2] = f_dead ? 1.0f : 0.0f;
-                                if (st) atomicOr(p.status + b, st);
-                                if (rank == 0) {
-                                    const double ll2 = (double)lg2(sum) + (double)M;
-                                    a.log_likelihood[b] = st ? -INFINITY : (float)(ll2 * kLn2);
-                                }
-                            }
-                            named_bar_sync(1, 32 * kHelpers);
-                        }
-                        if (rank == 1 || j > 0) {
-                            // gamma = alpha·p·beta / Z, exponents split over two factors
-                            const int kf = max(-252, min(252, EL - f_M));
-                            const int k1 = kf >> 1;
-                            const float fa = pow2i(max(-126, k1));
-                            const float fb = pow2i(max(-126, kf - k1)) * f_inv_sum;
-                            float g1[CPL], g2[CPL];
-#pragma unroll
-                            for (int i = 0; i < CPL; ++i) {
-                                const float va = VA[i] * fa;
-                                g1[i] = f_dead ? 0.0f : va * (pe[i] * fb);
-                                g2[i] = f_dead ? 0.0f : va * (ps[i] * fb);
-                            }
-                            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
-                            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
-                            // consistency: occupancy of the terminal cell (alpha side) / of frame 0
-                            // (beta side) must be 1 — these are independent likelihood estimates.
-                            if (!f_dead) {
-                                bool bad = false;
-                                if (rank == 0 && t == T - 1) {
-#pragma unroll
-                                    for (int i = 0; i < CPL; ++i)
-                                        if (c0 + i == U - 1) bad = !(fabsf(g1[i] - 1.0f) < kBfConsistency);
-                                }
-                                if (rank == 1 && t == 0 && lane == 0) bad = !(fabsf(g1[0] + g2[0] - 1.0f) < kBfConsistency);
-                                if (bad) atomicOr(p.status + b, (unsigned)kBfInconsistent);
+                        for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
+                        const float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
+                        const float sum = warp_sum(part);
+                        const unsigned bad = __ballot_sync(kFull, !finite);
+                        unsigned st = 0;
+                        if (bad) st |= kBfNonFinite;
+                        if (M <= kNoMass / 2 || !(sum > 0.0f)) st |= kBfNoMass;
+                        f_M = M;
+                        f_inv_sum = st ? 0.0f : 1.0f / sum;
+                        f_dead = st != 0;
+                        have_ll = true;
+                        if (lane == 0) {
+                            llinfo[0] = __int_as_float(M);
+                            llinfo[1] = f_inv_sum;
+                            llinfo[2] = f_dead ? 1.0f : 0.0f;
+                            if (st) atomicOr(p.status + b, st);
+                            if (rank == 0) {
+                                const double ll2 = (double)lg2(sum) + (double)M;
+                                a.log_likelihood[b] = st ? -INFINITY : (float)(ll2 * kLn2);
                             }
                         }
+                        named_bar_sync(1, 32 * kHelpers);
+                        // rank 0's meeting row only yields the likelihood: its gradients belong to rank 1
+                        if (rank == 0) r_first = 1;
+                    } else if (!have_ll) {  // wait for the log-likelihood of the meeting row
+                        named_bar_sync(1, 32 * kHelpers);
+                        f_M = __float_as_int(llinfo[0]);
+                        f_inv_sum = llinfo[1];
+                        f_dead = llinfo[2] != 0.0f;
+                        have_ll = true;
                     }
+                    PostCtx pc;
+                    pc.sp = sp; pc.off_e = off_e; pc.off_s = off_s; pc.off_x = off_x; pc.off_v = off_v;
+                    pc.max_u = max_u; pc.SU = SU; pc.UP = UP;
+                    pc.dir = dir; pc.rank = (int)rank; pc.lane = lane; pc.c0 = c0;
+                    pc.cnt = cnt; pc.t_base = P.t0 + dir * j0; pc.T = T; pc.U = U;
+                    pc.ex_state = ex_state; pc.f_M = f_M; pc.f_inv_sum = f_inv_sum; pc.f_dead = f_dead;
+                    pc.ge = ge; pc.gs = gs; pc.status = p.status + b;
+                    if (nr == kHalf && r_first == 0 && !(p.debug_skip & 4)) post_rows<CPL, kHalf>(pc, q0);
+                    else
+                        for (int r = r_first; r < nr; ++r) post_rows<CPL, 1>(pc, q0 + r);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(slot_free + slot));
+                    if (lane == 0) mbar_arrive_relaxed_n(smem_u32(slot_free + slot), 1);
                     if (half == 0) tl_mark(3, (int)kk, 2);
                     if (p.stats) st_post += clock64() - tq0;
                 }
@@ -840,7 +860,6 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
         o[0] = clock64() - st_t0;
         o[1] = st_wait[0]; o[2] = st_wait[1]; o[3] = st_wait[2]; o[4] = st_wait[3];
         o[5] = st_sync; o[6] = st_phase0; o[7] = st_prep * 1000000 + st_post / 1;
-        o[8] = st_min; o[9] = st_max; o[10] = st_n; o[11] = st_lt400; o[12] = st_lt800;
     }
 }
 

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
 }
 
 template <int CPL>
-__global__ void __launch_bounds__(kBfThreads) fb_bf_kernel(const BfParams p) {
+__global__ void __launch_bounds__(kBfThreads, 1) fb_bf_kernel(const BfParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kBfThreads) fb_bf_kernel(const BfParams p) {
         // Did either CTA flag the utterance?  If so the same cluster redoes it in the log domain.
         cluster.sync();
         const unsigned st = *reinterpret_cast<volatile unsigned*>(p.status + b);
-        if (st) {
+        if (st && !(p.debug_skip & 16)) {
             if (rank == 0 && tid == 0) atomicAdd(p.fallbacks, 1u);
             if (warp == 0) {
                 LogParams lp;
@@ -333,8 +333,7 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         if (const char* e = std::getenv("SSNT_BF_DEBUG_SKIP")) p.debug_skip = std::atoi(e);  // profiling aid
         const size_t smem = kBfHeaderBytes + (size_t)NS * stage_bytes;
         const int U = a.max_u;
-        if (U <= 32) launch_bf<1>(p, smem, stream);
-        else if (U <= 64) launch_bf<2>(p, smem, stream);
+        if (U <= 64) launch_bf<2>(p, smem, stream);
         else if (U <= 128) launch_bf<4>(p, smem, stream);
         else launch_bf<8>(p, smem, stream);
         return;

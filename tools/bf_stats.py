@@ -32,9 +32,6 @@ for rank in (0, 1):
         print(f"  {names[w]:9s} total {m[0]:9.0f} cyc | blocked: raw_full {m[1]:8.0f} prep_full {m[2]:8.0f} "
               f"state_full {m[3]:8.0f} slot_free {m[4]:8.0f} cluster_sync {m[5]:8.0f} | busy {m[0]-m[1]-m[2]-m[3]-m[4]-m[5]:8.0f} | phase1 ends at {m[6]:8.0f} | prep {s[:, rank, w, 7].div(1000000, rounding_mode='floor').mean():8.0f} post {s[:, rank, w, 7].remainder(1000000).mean():8.0f}")
 
-c = s[:, :, 0]
-print("chain full-stage row time: min %.0f  max %.0f  stages %.0f  min active lanes at stage start %.0f  <800cyc %.0f (averages over CTAs)" % tuple(c[:, :, i].mean().item() for i in (8, 9, 10, 11, 12)))
-
 if os.environ.get("TIMELINE"):
     print("stage | producer: wait_start issue | prep(pair of stage, half0): wait_start got_data done | chain: wait_start got_prep rows_done | post: wait_start got_state done")
     for k in list(range(0, 30)) + list(range(44, 70)) + list(range(94, 101)):
