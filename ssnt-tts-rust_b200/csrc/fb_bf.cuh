@@ -39,7 +39,7 @@ constexpr int kSlack = 0;         // a lane's frame never sits below its feeding
                                   // when decided, leaving ~100 bits for its growth until the next decision
 constexpr float kBfConsistency = 2e-5f;  // the three likelihood estimates must agree this well (typ. 1e-6)
 constexpr int kNoMass = -100000;  // exponent key of an all-zero lane
-constexpr int kBfHeaderBytes = 768;  // mbarriers (512) | llinfo (64) | log-domain re-run barriers (128) | pad
+constexpr int kBfHeaderBytes = 768;  // mbarriers (128) | flags (256) | llinfo | log-domain re-run barriers at 576 (128) | pad
 constexpr int kBfThreads = 256;   // warp 0 chain | warp 4 producer | warps 1-3,5-7 helpers
 constexpr int kHelpers = 6;
 constexpr int kPairs = 3;        // helper pairs; pair p owns stages p, p+3, ...
@@ -110,10 +110,14 @@ __device__ __forceinline__ float scale_pow2(float x, int k) {
 // Conversion of NR consecutive (in sweep order) rows of a stage from log-probabilities to
 // probabilities, in place, with the length masks: tokens >= U have e = s = 0, the last token and
 // the last frame cannot shift.  All loads first, then the EX2s, then the stores (ILP across rows).
-template <int CPL, int NR>
-__device__ __forceinline__ void prep_rows(float* e0, float* s0, const int in_stride, const int t_first,
+template <int CPL, int NR, bool FULL = false>
+__device__ __forceinline__ void prep_rows(float* e0, float* s0, int in_stride, const int t_first,
                                           const int dir, const int T, const bool (&me)[CPL],
-                                          const bool (&ms)[CPL], const int c0, const int max_u) {
+                                          const bool (&ms)[CPL], const int c0, int max_u) {
+    if (FULL) {  // max_u == 32*CPL: strides become immediates and the column bounds checks fold away
+        max_u = 32 * CPL;
+        in_stride = dir > 0 ? 32 * CPL : -32 * CPL;
+    }
     float E[NR][CPL], S[NR][CPL];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -310,8 +314,16 @@ struct PostCtx {
     unsigned* status;
 };
 
-template <int CPL, int NRP>
-__device__ __forceinline__ void post_rows(const PostCtx& c, const int q0) {
+template <int CPL, int NRP, bool FULL = false, bool CHECK = true>
+__device__ __forceinline__ void post_rows(const PostCtx& cx, const int q0) {
+    PostCtx c = cx;
+    if (FULL) {  // max_u == 32*CPL: strides become immediates and the column bounds checks fold away
+        c.max_u = 32 * CPL;
+        c.SU = 32 * CPL + 32;
+        c.UP = 32 * CPL;
+        c.off_e = 0; c.off_s = kG * 32 * CPL; c.off_x = 2 * kG * 32 * CPL;
+        c.off_v = 2 * kG * 32 * CPL + kG * (32 * CPL + 32);
+    }
     float E[NRP][CPL], S[NRP][CPL], VA[NRP][CPL], VB[NRP][CPL];
     int exA[NRP], exB[NRP];
 #pragma unroll
@@ -361,7 +373,7 @@ __device__ __forceinline__ void post_rows(const PostCtx& c, const int q0) {
         store_cells_cs<CPL>(c.gs + (size_t)t * c.max_u, c.c0, c.max_u, g2);
         // consistency: occupancy of the terminal cell (alpha side) / of frame 0 (beta side) must
         // be 1 — these are independent likelihood estimates.
-        if (!c.f_dead && (t == c.T - 1 || t == 0)) {
+        if (CHECK && !c.f_dead && (t == c.T - 1 || t == 0)) {
             bool bad = false;
             if (c.rank == 0 && t == c.T - 1) {
 #pragma unroll
@@ -371,6 +383,44 @@ __device__ __forceinline__ void post_rows(const PostCtx& c, const int q0) {
             if (c.rank == 1 && t == 0 && c.lane == 0) bad = !(fabsf(g1[0] + g2[0] - 1.0f) < kBfConsistency);
             if (bad) atomicOr(c.status, (unsigned)kBfInconsistent);
         }
+    }
+}
+
+// ---- shared-memory flags ---------------------------------------------------------------------------
+// Hand-offs that involve the recursion warp are plain shared-memory words, not mbarriers: an
+// mbarrier probe costs 90-150 cycles on an idle SM and several hundred while six helper warps poll
+// the same unit (measured: ~1400 cycles of fixed cost per round), and it cannot be issued ahead of
+// its use.  A flag is an ordinary LDS (29 cycles) that the recursion warp issues a round early.
+__device__ __forceinline__ int flag_load(const int* f) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(f)) : "memory");
+    return v;
+}
+__device__ __forceinline__ int2 flag_load2(const int* f) {
+    int2 v;
+    asm volatile("ld.volatile.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(f)) : "memory");
+    return v;
+}
+// Publishes `v` after everything the warp wrote before (call by one lane after __syncwarp()).
+__device__ __forceinline__ void flag_publish(int* f, int v) {
+    __threadfence_block();
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(f)), "r"(v) : "memory");
+}
+
+// Phase-1 duty of the helpers' "post" slot: copy NR state rows of a stage (values + the lane
+// exponents of the round) from shared memory to the global scratch rows the partner CTA reads.
+template <int CPL, int NR, bool FULL = false>
+__device__ __forceinline__ void copy_out_rows(const float* st0, float* g0, const long long gstride, const int ex,
+                                              const int c0, int max_u, int UP, const int lane) {
+    if (FULL) { max_u = 32 * CPL; UP = 32 * CPL; }
+    float V[NR][CPL];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) load_cells<CPL>(st0 + r * max_u, c0, max_u, 0.0f, V[r]);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        float* dst = g0 + (long long)r * gstride;
+        store_cells<CPL>(dst, c0, max_u, V[r]);
+        reinterpret_cast<int*>(dst)[UP + lane] = ex;
     }
 }
 
@@ -390,25 +440,21 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
     const int c0 = lane * CPL;
 
     // ---- shared memory carve-up -------------------------------------------------------------------
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // 4 x NS barriers (NS <= 16)
-    uint64_t* raw_full = bars;
-    uint64_t* prep_full = bars + 16;
-    uint64_t* state_full = bars + 32;
-    uint64_t* slot_free = bars + 48;
-    float* llinfo = reinterpret_cast<float*>(smem_raw + 512);  // [0] M (int bits) [1] 1/sum [2] dead
+    // header: raw_full mbarriers [16] | prep_flag [16][2] | state_flag [16] | done [8] | llinfo | (log re-run barriers at 576)
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem_raw);           // TMA → prep helpers
+    int* prep_flag = reinterpret_cast<int*>(smem_raw + 128);              // [slot][half] = use+1 once prepped
+    int* state_flag = reinterpret_cast<int*>(smem_raw + 256);             // [slot] = use+1 once the state rows are written
+    int* done = reinterpret_cast<int*>(smem_raw + 320);                   // [helper] = 1 + last global stage it finished
+    float* llinfo = reinterpret_cast<float*>(smem_raw + 384);             // [0] M (int bits) [1] 1/sum [2] dead
     float* ring = reinterpret_cast<float*>(smem_raw + kBfHeaderBytes);
     // per slot: e[8][max_u] | s[8][max_u] | x[8][SU] | state[8][max_u] | state_exp[32]
     const int off_e = 0, off_s = kG * max_u, off_x = 2 * kG * max_u, off_v = off_x + kG * SU,
               off_ve = off_v + kG * max_u;
     const int stage_floats = off_ve + 32;
 
+    if (tid < 64) reinterpret_cast<int*>(smem_raw + 128)[tid] = 0;  // all flags
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(smem_u32(raw_full + s), 1);
-            mbar_init(smem_u32(prep_full + s), 2);
-            mbar_init(smem_u32(state_full + s), 1);
-            mbar_init(smem_u32(slot_free + s), 2);
-        }
+        for (int s = 0; s < NS; ++s) mbar_init(smem_u32(raw_full + s), 1);
         fence_mbar_init();
         if (rank == 0) p.status[b] = p.force_fallback ? (unsigned)kBfForced : 0u;
     }
@@ -432,7 +478,7 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
     auto slot_of = [&](unsigned kk) { return (int)(kk % (unsigned)NS); };
     auto use_of = [&](unsigned kk) { return kk / (unsigned)NS; };
     auto slot_ptr = [&](int slot) { return ring + (size_t)slot * stage_floats; };
-    // profiling aid: cycles spent blocked on each kind of barrier, per warp
+    // profiling aid: cycles spent blocked on each kind of hand-off, per warp
     long long st_wait[4] = {0, 0, 0, 0};
     const long long st_t0 = p.stats ? clock64() : 0;
     long long st_sync = 0, st_phase0 = 0, st_prep = 0, st_post = 0;
@@ -446,15 +492,9 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
             cluster.sync();
         }
     };
-    long long* tl = (p.stats && blockIdx.x == 0) ? p.stats + (size_t)gridDim.x * 8 * 16 : nullptr;  // timeline of CTA 0
+    long long* tl = (p.stats && blockIdx.x == 0 && (p.debug_skip & 128)) ? p.stats + (size_t)gridDim.x * 8 * 16 : nullptr;  // timeline of CTA 0
     auto tl_mark = [&](int role, int stage, int ev) {
         if (tl && lane == 0 && stage < 256) tl[(role * 256 + stage) * 4 + ev] = clock64() - st_t0;
-    };
-    // Warp-uniform wait (see mbar_wait_warp): keeps the role's warp converged.
-    auto timed_wait = [&](int kind, uint32_t bar, uint32_t parity) {
-        const long long t0 = p.stats ? clock64() : 0;
-        mbar_wait_warp(bar, parity);
-        if (p.stats) st_wait[kind] += clock64() - t0;
     };
 
     // =================================================================================================
@@ -486,9 +526,9 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
             // Four stages are issued per round: lane l handles array (l % 3) of stage (l / 3) of the
             // batch, so one cp.async.bulk instruction starts up to 12 copies (the issue cost is per
             // instruction, ~150-300 cycles, not per copy).  Lanes 12-13 issue the L2 prefetches.  No
-            // proxy fence per stage: a slot is only refilled after its readers arrived on slot_free,
-            // and a fence.proxy.async here would wait for the copies still in flight, collapsing the
-            // ring to a single outstanding stage.
+            // proxy fence per stage: a slot is only refilled after the helpers that read it last
+            // published `done`, and a fence.proxy.async here would wait for the copies still in
+            // flight, collapsing the ring to a single outstanding stage.
             constexpr int NB = 4;
             const int jb = lane / 3, arr = lane - jb * 3;
             const int narr = P.with_x ? 3 : 2;
@@ -497,7 +537,6 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                 const bool mine = lane < 3 * NB && k < P.nst && arr < narr;
                 const unsigned kk = kg + (unsigned)k;
                 const int slot = (int)(kk % (unsigned)NS);
-                const unsigned use = kk / (unsigned)NS;
                 const int j0 = k * kG;
                 const int cnt = min(kG, P.n - j0);
                 const int r0 = dir > 0 ? P.t0 + j0 : P.t0 - j0 - cnt + 1;
@@ -506,7 +545,18 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                 const uint32_t bytes_x = P.with_x ? (uint32_t)cnt * (uint32_t)SU * 4u : 0u;
                 if (lane == 0) tl_mark(1, (int)kk, 0);
                 if (mine && arr == 0) {
-                    if (use > 0) mbar_wait_backoff(smem_u32(slot_free + slot), (use - 1) & 1u, (unsigned)p.pf_sleep_ns);
+                    if (kk >= (unsigned)NS) {
+                        // previous occupant of the slot: global stage kk - NS, owned (both halves) by
+                        // helper pair (its phase-local index % 3)
+                        const int old = (int)kk - NS;
+                        const int old_local = old < ph[0].nst ? old : old - ph[0].nst;
+                        const int* d = done + 2 * (old_local % kPairs);
+                        for (;;) {
+                            const int2 v = flag_load2(d);
+                            if (v.x > old && v.y > old) break;
+                            __nanosleep((unsigned)p.pf_sleep_ns);
+                        }
+                    }
                     mbar_expect_tx(bar, 2u * bytes_e + bytes_x);
                 }
                 __syncwarp();
@@ -597,32 +647,33 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                 fence_proxy_async();
                 timed_cluster_sync();
             }
-            const int Pn = ph[phase].n, Pt0 = ph[phase].t0, Pnst = ph[phase].nst;
+            const int Pn = ph[phase].n, Pnst = ph[phase].nst;
             int slot = (int)(kg % (unsigned)NS);
-            unsigned par = (kg / (unsigned)NS) & 1u;
-            bool pre0 = false, pre1 = false;  // prefetched state of the next round's barriers
+            int use1 = (int)(kg / (unsigned)NS) + 1;  // value the slot's flags take once it is ready
+            // flags of this round's slots, loaded one round ahead
+            int2 fA = make_int2(0, 0), fB = make_int2(0, 0);
             for (int k = 0; k < Pnst;) {
-                const bool two = full_u && Pn - k * kG >= 2 * kG && !(p.debug_skip & 2);  // fast path: two full stages per round
+                const bool two = full_u && Pn - k * kG >= 2 * kG && !(p.debug_skip & 2);  // two full stages per round
                 const int slot2 = slot + 1 == NS ? 0 : slot + 1;
-                const unsigned par2 = slot + 1 == NS ? par ^ 1u : par;
+                const int use2 = slot + 1 == NS ? use1 + 1 : use1;
                 tl_mark(0, (int)kg + k, 0);
                 {
                     const long long t0 = p.stats ? clock64() : 0;
-                    if (!__all_sync(kFull, pre0)) mbar_wait_warp(smem_u32(prep_full + slot), par);
-                    if (two && !__all_sync(kFull, pre1)) mbar_wait_warp(smem_u32(prep_full + slot2), par2);
+                    while (!__all_sync(kFull, fA.x >= use1 && fA.y >= use1)) fA = flag_load2(prep_flag + 2 * slot);
+                    if (two)
+                        while (!__all_sync(kFull, fB.x >= use2 && fB.y >= use2)) fB = flag_load2(prep_flag + 2 * slot2);
                     if (p.stats) st_wait[1] += clock64() - t0;
                 }
                 tl_mark(0, (int)kg + k, 1);
                 const int adv = two ? 2 : 1;
-                // probe the barriers of the next round now; the answer is consumed a round later
+                // request the flags of the next round's slots now; they are looked at a round later
+                int slot_n = slot, use_n = use1;
+                for (int z = 0; z < adv; ++z)
+                    if (++slot_n == NS) { slot_n = 0; ++use_n; }
                 {
-                    int s3 = slot, q3 = (int)par;
-                    for (int z = 0; z < adv; ++z)
-                        if (++s3 == NS) { s3 = 0; q3 ^= 1; }
-                    const int s4 = s3 + 1 == NS ? 0 : s3 + 1;
-                    const int q4 = s3 + 1 == NS ? q3 ^ 1 : q3;
-                    pre0 = !(p.debug_skip & 1) && k + adv < Pnst && mbar_test(smem_u32(prep_full + s3), (uint32_t)q3);
-                    pre1 = !(p.debug_skip & 1) && k + adv + 1 < Pnst && mbar_test(smem_u32(prep_full + s4), (uint32_t)q4);
+                    const int s4 = slot_n + 1 == NS ? 0 : slot_n + 1;
+                    fA = flag_load2(prep_flag + 2 * slot_n);
+                    fB = flag_load2(prep_flag + 2 * s4);
                 }
                 float* spA = slot_ptr(slot);
                 float* spB = slot_ptr(slot2);
@@ -630,39 +681,27 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                 const int cnt = min(kG, Pn - j0);
                 const long long tr0 = p.stats ? clock64() : 0;
                 apply_decision();
-                if (phase == 1) {
-                    reinterpret_cast<int*>(spA + off_ve)[lane] = ex;
-                    if (two) reinterpret_cast<int*>(spB + off_ve)[lane] = ex;
-                }
+                reinterpret_cast<int*>(spA + off_ve)[lane] = ex;
+                if (two) reinterpret_cast<int*>(spB + off_ve)[lane] = ex;
                 int own = kNoMass, nbmag = kNoMass;
                 auto d1 = [&]() { decide_1(own, nbmag); };
                 auto d2 = [&]() { decide_2(own, nbmag); };
-                // first row of the stage in sweep order; state rows: phase 1 → global scratch
-                // (alpha(t) → row t, beta(t+1) → row t+1), phase 2 → the slot's shared state rows.
+                const long long tr1 = p.stats ? clock64() : 0;
+                st_post += tr1 - tr0;
+                // first row of the stage in sweep order (rank 1 walks the slot's rows backwards);
+                // the state rows go to the slot's shared state rows in both phases
                 const int eo = dir > 0 ? 0 : (kG - 1) * max_u;
-                float* st_g = scr + (size_t)(Pt0 + dir * j0 + (rank == 0 ? 0 : 1)) * SU;
-                if (full_u && cnt == kG && !(p.debug_skip & 8)) {
+                if (full_u && cnt == kG) {
                     const float* eA = spA + off_e + eo;
                     const float* sA = spA + off_s + eo;
                     const float* eB = spB + off_e + eo;
                     const float* sB = spB + off_s + eo;
-                    float* st_g2 = st_g + (long long)dir * kG * SU;
                     if (two) {
-                        if (rank == 0) {
-                            if (phase == 0) chain_round_skew<CPL, 0, false, 16>(cs, g, eA, sA, st_g, ex, lane, d1, d2, eB, sB, st_g2);
-                            else chain_round_skew<CPL, 0, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
-                        } else {
-                            if (phase == 0) chain_round_skew<CPL, 1, false, 16>(cs, g, eA, sA, st_g, ex, lane, d1, d2, eB, sB, st_g2);
-                            else chain_round_skew<CPL, 1, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
-                        }
+                        if (rank == 0) chain_round_skew<CPL, 0, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
+                        else chain_round_skew<CPL, 1, true, 16>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2, eB, sB, spB + off_v);
                     } else {
-                        if (rank == 0) {
-                            if (phase == 0) chain_round_skew<CPL, 0, false, 8>(cs, g, eA, sA, st_g, ex, lane, d1, d2);
-                            else chain_round_skew<CPL, 0, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
-                        } else {
-                            if (phase == 0) chain_round_skew<CPL, 1, false, 8>(cs, g, eA, sA, st_g, ex, lane, d1, d2);
-                            else chain_round_skew<CPL, 1, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
-                        }
+                        if (rank == 0) chain_round_skew<CPL, 0, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
+                        else chain_round_skew<CPL, 1, true, 8>(cs, g, eA, sA, spA + off_v, ex, lane, d1, d2);
                     }
                 } else {
                     // generic rows: short last stage of a phase, or max_u < 32*CPL
@@ -677,43 +716,38 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                         const float P = (rank == 0 && pc < max_u) ? sr[pc] : 0.0f;
                         if (rank == 0) skew_step<CPL, 0>(cs, E, S, P, g, out);
                         else skew_step<CPL, 1>(cs, E, S, P, g, out);
-                        float* dst = phase == 0 ? st_g + (long long)q * dir * SU : spA + off_v + q * max_u;
-                        store_cells<CPL>(dst, c0, max_u, out);
-                        if (phase == 0) reinterpret_cast<int*>(dst)[UP + lane] = ex;
+                        store_cells<CPL>(spA + off_v + q * max_u, c0, max_u, out);
                     }
                     decide_1(own, nbmag);
                     decide_2(own, nbmag);
                 }
-                if (p.stats) st_prep += clock64() - tr0;
+                const long long tr2 = p.stats ? clock64() : 0;
+                st_prep += tr2 - tr1;
                 __syncwarp();
                 if (lane == 0) {
-                    if (phase == 0) {
-                        // nobody reads state rows in phase 1; the slot is free once its rows were read
-                        mbar_arrive_relaxed_n(smem_u32(state_full + slot), 1);
-                        mbar_arrive_relaxed_n(smem_u32(slot_free + slot), 2);
-                        if (two) {
-                            mbar_arrive_relaxed_n(smem_u32(state_full + slot2), 1);
-                            mbar_arrive_relaxed_n(smem_u32(slot_free + slot2), 2);
-                        }
-                    } else {
-                        mbar_arrive(smem_u32(state_full + slot));
-                        if (two) mbar_arrive(smem_u32(state_full + slot2));
-                    }
+                    __threadfence_block();
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(state_flag + slot)), "r"(use1) : "memory");
+                    if (two)
+                        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(state_flag + slot2)), "r"(use2) : "memory");
                 }
                 tl_mark(0, (int)kg + k, 2);
                 if (two) tl_mark(0, (int)kg + k + 1, 2);
+                if (p.stats) st_wait[3] += clock64() - tr2;
                 k += adv;
-                for (int z = 0; z < adv; ++z)
-                    if (++slot == NS) { slot = 0; par ^= 1u; }
+                slot = slot_n;
+                use1 = use_n;
             }
             kg += (unsigned)Pnst;
         }
     } else {
         // ------------------------------- helpers -------------------------------
-        // Six helper warps form three pairs; pair p owns stages k = p, p+3, p+6, ... and each warp
-        // of the pair owns one half (4 rows) of the stage, processed together for ILP.
+        // Six helper warps form three pairs; pair p owns stages k = p, p+3, p+6, ... of each phase and
+        // each warp of the pair owns one half (4 rows) of the stage, processed together for ILP.
+        // Per stage: prep (log-probs → probabilities, in place) ahead of the recursion, and behind it
+        // "post": phase 1 copies the state rows to the global scratch, phase 2 emits the gradients.
         const int h = warp < 4 ? warp - 1 : warp - 2;  // warps 1,2,3,5,6,7 → 0..5
         const int pair = h >> 1, half = h & 1;
+        const bool full_u = max_u == 32 * CPL;
         bool me[CPL], ms[CPL];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
@@ -722,19 +756,27 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
         }
         unsigned kg = 0;
         for (int phase = 0; phase < 2; ++phase) {
-            if (phase == 1) timed_cluster_sync();
+            if (phase == 1) {
+                __threadfence();       // this warp's scratch rows → visible to the partner CTA's TMA reads
+                fence_proxy_async();
+                timed_cluster_sync();
+            }
             const Phase& P = ph[phase];
             float f_inv_sum = 0.0f;
             int f_M = 0;
             bool f_dead = false, have_ll = false;
-            for (int it = pair; it < P.nst + (phase == 1 ? kPairs : 0); it += kPairs) {
-                // ---- prep(it): log-probs → probabilities, in place ----
+            for (int it = pair; it < P.nst + kPairs; it += kPairs) {
+                // ---- prep(it) ----
                 if (it < P.nst) {
                     const int k = it;
                     const unsigned kk = kg + (unsigned)k;
                     const int slot = slot_of(kk);
                     if (half == 0) tl_mark(2, (int)kk, 0);
-                    timed_wait(0, smem_u32(raw_full + slot), use_of(kk) & 1u);
+                    {
+                        const long long t0 = p.stats ? clock64() : 0;
+                        mbar_wait_warp(smem_u32(raw_full + slot), use_of(kk) & 1u);
+                        if (p.stats) st_wait[0] += clock64() - t0;
+                    }
                     if (half == 0) tl_mark(2, (int)kk, 1);
                     const long long tp0 = p.stats ? clock64() : 0;
                     float* sp = slot_ptr(slot);
@@ -746,23 +788,32 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                     float* e0 = sp + off_e + idx0 * max_u;
                     float* s0 = sp + off_s + idx0 * max_u;
                     const int t0r = P.t0 + dir * (j0 + q0);
-                    if (nr == kHalf) prep_rows<CPL, kHalf>(e0, s0, dir * max_u, t0r, dir, T, me, ms, c0, max_u);
+                    if (p.debug_skip & 32) {
+                    } else if (nr == kHalf && full_u) {
+                        if (dir > 0) prep_rows<CPL, kHalf, true>(e0, s0, 0, t0r, 1, T, me, ms, c0, max_u);
+                        else prep_rows<CPL, kHalf, true>(e0, s0, 0, t0r, -1, T, me, ms, c0, max_u);
+                    } else if (nr == kHalf) prep_rows<CPL, kHalf>(e0, s0, dir * max_u, t0r, dir, T, me, ms, c0, max_u);
                     else
                         for (int r = 0; r < nr; ++r)
                             prep_rows<CPL, 1>(e0 + r * dir * max_u, s0 + r * dir * max_u, dir * max_u, t0r + dir * r,
                                               dir, T, me, ms, c0, max_u);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(prep_full + slot));
+                    if (lane == 0) flag_publish(prep_flag + 2 * slot + half, (int)use_of(kk) + 1);
                     if (half == 0) tl_mark(2, (int)kk, 2);
                     if (p.stats) st_prep += clock64() - tp0;
                 }
-                // ---- post(it - kPairs): gradients (phase 2 only) ----
-                if (phase == 1 && it >= kPairs) {
+                // ---- post(it - kPairs) ----
+                if (it >= kPairs) {
                     const int k = it - kPairs;
                     const unsigned kk = kg + (unsigned)k;
                     const int slot = slot_of(kk);
+                    const int need = (int)use_of(kk) + 1;
                     if (half == 0) tl_mark(3, (int)kk, 0);
-                    timed_wait(2, smem_u32(state_full + slot), use_of(kk) & 1u);
+                    {
+                        const long long t0 = p.stats ? clock64() : 0;
+                        while (flag_load(state_flag + slot) < need) __nanosleep(40);
+                        if (p.stats) st_wait[2] += clock64() - t0;
+                    }
                     if (half == 0) tl_mark(3, (int)kk, 1);
                     const long long tq0 = p.stats ? clock64() : 0;
                     float* sp = slot_ptr(slot);
@@ -771,82 +822,101 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                     const int q0 = half * kHalf;
                     const int nr = max(0, min(kHalf, cnt - q0));
                     const int ex_state = reinterpret_cast<const int*>(sp + off_ve)[lane];
-                    const bool ll_owner = (k == 0 && half == 0);
-                    int r_first = 0;
-                    if (ll_owner) {
-                        // log-likelihood from the meeting row j = 0: Z = sum_u alpha(m-1,u)·beta(m-1,u)
-                        const int idx = dir > 0 ? 0 : cnt - 1;
-                        float E[CPL], S[CPL], VA[CPL], VB[CPL];
-                        load_cells<CPL>(sp + off_e + idx * max_u, c0, max_u, 0.0f, E);
-                        load_cells<CPL>(sp + off_s + idx * max_u, c0, max_u, 0.0f, S);
-                        const float* xrow = sp + off_x + idx * SU;
-                        const int ex_x = reinterpret_cast<const int*>(xrow)[UP + lane];
-                        int exA, exB;
-                        if (rank == 0) {
-                            load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VA);
-                            load_cells<CPL>(xrow, c0, max_u, 0.0f, VB);
-                            exA = ex_state; exB = ex_x;
-                        } else {
-                            load_cells<CPL>(xrow, c0, max_u, 0.0f, VA);
-                            load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VB);
-                            exA = ex_x; exB = ex_state;
-                        }
-                        const int exBn = __shfl_down_sync(kFull, exB, 1);
-                        float vbn_edge = scale_pow2(__shfl_down_sync(kFull, VB[0], 1), exBn - exB);
-                        if (lane == 31) vbn_edge = 0.0f;
-                        const int EL = exA + exB;
-                        float w = 0.0f;
-#pragma unroll
-                        for (int i = 0; i < CPL; ++i) {
-                            const float nb = (i + 1 < CPL) ? VB[i + 1] : vbn_edge;
-                            w += VA[i] * (E[i] * VB[i] + S[i] * nb);
-                        }
-                        const bool finite = w == w && w < 3.0e38f;
-                        int M = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
-                        const float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
-                        const float sum = warp_sum(part);
-                        const unsigned bad = __ballot_sync(kFull, !finite);
-                        unsigned st = 0;
-                        if (bad) st |= kBfNonFinite;
-                        if (M <= kNoMass / 2 || !(sum > 0.0f)) st |= kBfNoMass;
-                        f_M = M;
-                        f_inv_sum = st ? 0.0f : 1.0f / sum;
-                        f_dead = st != 0;
-                        have_ll = true;
-                        if (lane == 0) {
-                            llinfo[0] = __int_as_float(M);
-                            llinfo[1] = f_inv_sum;
-                            llinfo[2] = f_dead ? 1.0f : 0.0f;
-                            if (st) atomicOr(p.status + b, st);
+                    if (phase == 0) {
+                        // state row q = alpha(t) → scratch row t (rank 0), beta(t+1) → row t+1 (rank 1)
+                        const int t0r = P.t0 + dir * (j0 + q0) + (rank == 0 ? 0 : 1);
+                        float* g0 = scr + (size_t)t0r * SU;
+                        const float* st0 = sp + off_v + q0 * max_u;
+                        if (nr == kHalf && full_u) copy_out_rows<CPL, kHalf, true>(st0, g0, (long long)dir * SU, ex_state, c0, max_u, UP, lane);
+                        else if (nr == kHalf) copy_out_rows<CPL, kHalf>(st0, g0, (long long)dir * SU, ex_state, c0, max_u, UP, lane);
+                        else
+                            for (int r = 0; r < nr; ++r)
+                                copy_out_rows<CPL, 1>(st0 + r * max_u, g0 + (long long)r * dir * SU, 0, ex_state, c0, max_u, UP, lane);
+                    } else {
+                        const bool ll_owner = (k == 0 && half == 0);
+                        int r_first = 0;
+                        if (ll_owner) {
+                            // log-likelihood from the meeting row j = 0: Z = sum_u alpha(m-1,u)·beta(m-1,u)
+                            const int idx = dir > 0 ? 0 : cnt - 1;
+                            float E[CPL], S[CPL], VA[CPL], VB[CPL];
+                            load_cells<CPL>(sp + off_e + idx * max_u, c0, max_u, 0.0f, E);
+                            load_cells<CPL>(sp + off_s + idx * max_u, c0, max_u, 0.0f, S);
+                            const float* xrow = sp + off_x + idx * SU;
+                            const int ex_x = reinterpret_cast<const int*>(xrow)[UP + lane];
+                            int exA, exB;
                             if (rank == 0) {
-                                const double ll2 = (double)lg2(sum) + (double)M;
-                                a.log_likelihood[b] = st ? -INFINITY : (float)(ll2 * kLn2);
+                                load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VA);
+                                load_cells<CPL>(xrow, c0, max_u, 0.0f, VB);
+                                exA = ex_state; exB = ex_x;
+                            } else {
+                                load_cells<CPL>(xrow, c0, max_u, 0.0f, VA);
+                                load_cells<CPL>(sp + off_v, c0, max_u, 0.0f, VB);
+                                exA = ex_x; exB = ex_state;
                             }
+                            const int exBn = __shfl_down_sync(kFull, exB, 1);
+                            float vbn_edge = scale_pow2(__shfl_down_sync(kFull, VB[0], 1), exBn - exB);
+                            if (lane == 31) vbn_edge = 0.0f;
+                            const int EL = exA + exB;
+                            float w = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < CPL; ++i) {
+                                const float nb = (i + 1 < CPL) ? VB[i + 1] : vbn_edge;
+                                w += VA[i] * (E[i] * VB[i] + S[i] * nb);
+                            }
+                            const bool finite = w == w && w < 3.0e38f;
+                            int M = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
+                            const float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
+                            const float sum = warp_sum(part);
+                            const unsigned bad = __ballot_sync(kFull, !finite);
+                            unsigned st = 0;
+                            if (bad) st |= kBfNonFinite;
+                            if (M <= kNoMass / 2 || !(sum > 0.0f)) st |= kBfNoMass;
+                            f_M = M;
+                            f_inv_sum = st ? 0.0f : 1.0f / sum;
+                            f_dead = st != 0;
+                            have_ll = true;
+                            if (lane == 0) {
+                                llinfo[0] = __int_as_float(M);
+                                llinfo[1] = f_inv_sum;
+                                llinfo[2] = f_dead ? 1.0f : 0.0f;
+                                if (st) atomicOr(p.status + b, st);
+                                if (rank == 0) {
+                                    const double ll2 = (double)lg2(sum) + (double)M;
+                                    a.log_likelihood[b] = st ? -INFINITY : (float)(ll2 * kLn2);
+                                }
+                            }
+                            named_bar_sync(1, 32 * kHelpers);
+                            // rank 0's meeting row only yields the likelihood: its gradients belong to rank 1
+                            if (rank == 0) r_first = 1;
+                        } else if (!have_ll) {  // wait for the log-likelihood of the meeting row
+                            named_bar_sync(1, 32 * kHelpers);
+                            f_M = __float_as_int(llinfo[0]);
+                            f_inv_sum = llinfo[1];
+                            f_dead = llinfo[2] != 0.0f;
+                            have_ll = true;
                         }
-                        named_bar_sync(1, 32 * kHelpers);
-                        // rank 0's meeting row only yields the likelihood: its gradients belong to rank 1
-                        if (rank == 0) r_first = 1;
-                    } else if (!have_ll) {  // wait for the log-likelihood of the meeting row
-                        named_bar_sync(1, 32 * kHelpers);
-                        f_M = __float_as_int(llinfo[0]);
-                        f_inv_sum = llinfo[1];
-                        f_dead = llinfo[2] != 0.0f;
-                        have_ll = true;
+                        PostCtx pc;
+                        pc.sp = sp; pc.off_e = off_e; pc.off_s = off_s; pc.off_x = off_x; pc.off_v = off_v;
+                        pc.max_u = max_u; pc.SU = SU; pc.UP = UP;
+                        pc.dir = dir; pc.rank = (int)rank; pc.lane = lane; pc.c0 = c0;
+                        pc.cnt = cnt; pc.t_base = P.t0 + dir * j0; pc.T = T; pc.U = U;
+                        pc.ex_state = ex_state; pc.f_M = f_M; pc.f_inv_sum = f_inv_sum; pc.f_dead = f_dead;
+                        pc.ge = ge; pc.gs = gs; pc.status = p.status + b;
+                        if (p.debug_skip & 64) {
+                        } else if (nr == kHalf && r_first == 0 && full_u && k + 1 < P.nst && !(p.debug_skip & 4)) {
+                            // hot path: full stage that does not hold the sweep's last row (no consistency check)
+                            if (rank == 0) { pc.dir = 1; pc.rank = 0; post_rows<CPL, kHalf, true, false>(pc, q0); }
+                            else { pc.dir = -1; pc.rank = 1; post_rows<CPL, kHalf, true, false>(pc, q0); }
+                        } else if (nr == kHalf && r_first == 0 && !(p.debug_skip & 4)) post_rows<CPL, kHalf>(pc, q0);
+                        else
+                            for (int r = r_first; r < nr; ++r) post_rows<CPL, 1>(pc, q0 + r);
                     }
-                    PostCtx pc;
-                    pc.sp = sp; pc.off_e = off_e; pc.off_s = off_s; pc.off_x = off_x; pc.off_v = off_v;
-                    pc.max_u = max_u; pc.SU = SU; pc.UP = UP;
-                    pc.dir = dir; pc.rank = (int)rank; pc.lane = lane; pc.c0 = c0;
-                    pc.cnt = cnt; pc.t_base = P.t0 + dir * j0; pc.T = T; pc.U = U;
-                    pc.ex_state = ex_state; pc.f_M = f_M; pc.f_inv_sum = f_inv_sum; pc.f_dead = f_dead;
-                    pc.ge = ge; pc.gs = gs; pc.status = p.status + b;
-                    if (nr == kHalf && r_first == 0 && !(p.debug_skip & 4)) post_rows<CPL, kHalf>(pc, q0);
-                    else
-                        for (int r = r_first; r < nr; ++r) post_rows<CPL, 1>(pc, q0 + r);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_relaxed_n(smem_u32(slot_free + slot), 1);
+                    // the slot may be refilled once both halves are through with it (no release needed for
+                    // the global stores: `done` only guards the slot's shared memory)
+                    if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(done + h)), "r"((int)kk + 1) : "memory");
                     if (half == 0) tl_mark(3, (int)kk, 2);
                     if (p.stats) st_post += clock64() - tq0;
                 }

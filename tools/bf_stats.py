@@ -30,7 +30,7 @@ for rank in (0, 1):
     for w in range(8):
         m = s[:, rank, w].mean(0)
         print(f"  {names[w]:9s} total {m[0]:9.0f} cyc | blocked: raw_full {m[1]:8.0f} prep_full {m[2]:8.0f} "
-              f"state_full {m[3]:8.0f} slot_free {m[4]:8.0f} cluster_sync {m[5]:8.0f} | busy {m[0]-m[1]-m[2]-m[3]-m[4]-m[5]:8.0f} | phase1 ends at {m[6]:8.0f} | prep {s[:, rank, w, 7].div(1000000, rounding_mode='floor').mean():8.0f} post {s[:, rank, w, 7].remainder(1000000).mean():8.0f}")
+              f"state_full {m[3]:8.0f} slot_free/handoff {m[4]:8.0f} cluster_sync {m[5]:8.0f} | busy {m[0]-m[1]-m[2]-m[3]-m[4]-m[5]:8.0f} | phase1 ends at {m[6]:8.0f} | prep {s[:, rank, w, 7].div(1000000, rounding_mode='floor').mean():8.0f} post {s[:, rank, w, 7].remainder(1000000).mean():8.0f}")
 
 if os.environ.get("TIMELINE"):
     print("stage | producer: wait_start issue | prep(pair of stage, half0): wait_start got_data done | chain: wait_start got_prep rows_done | post: wait_start got_state done")
