@@ -341,7 +341,8 @@ def run_b200(args):
             "global_batch": world * B, "parallelism": f"batch-sharded dp{world}, all-reduce of the scalar loss only",
             "l2_policy": f"rotating {nsets} independent input/output/scratch sets "
                          f"({nsets * set_bytes / 1e6:.0f} MB > 3x 126 MB L2); inputs come from HBM every step",
-            "fb_kernel": {2: "fb_bf_kernel (block-float, warp-specialised cluster of 2 CTAs, TMA ring)",
+            "fb_kernel": {4: "fb_split_kernel (block-float; cluster of 4 CTAs per utterance: 2 recursion CTAs + 2 helper CTAs, TMA ring, DSMEM flags)",
+                          2: "fb_bf_kernel (block-float, warp-specialised cluster of 2 CTAs, TMA ring)",
                           1: "fb_log_warp_kernel (log domain, cluster of 2 warps, TMA ring)",
                           0: "fb_generic_kernel"}.get(kernel_kind),
             "loss_check": final_loss,
@@ -381,7 +382,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--fb-kernel", type=int, default=-1, help="-1 auto, 0 generic, 1 log-warp, 2 block-float")
+    ap.add_argument("--fb-kernel", type=int, default=-1, help="-1 auto, 0 generic, 1 log-warp, 2 block-float fused, 4 block-float split-role")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -238,13 +238,14 @@ __device__ __forceinline__ void skew_step(ChainState<CPL>& cs, const float (&E)[
 // memory backwards); rows [8, 16) of a 16-row round come from e1/s1.  State rows go to st0 + q*stride
 // (shared, stride max_u) or to the global scratch (stride +-SU, lane exponents behind the row).
 // Hooks: h1 after row NR-3, h2 after row NR-2 (the two halves of the re-normalisation decision).
-template <int CPL, int RANK, bool TO_SMEM, int NR, typename H1, typename H2>
+// FWD: both directions walk their stage rows forwards in memory (stages stored in sweep order).
+template <int CPL, int RANK, bool TO_SMEM, int NR, typename H1, typename H2, bool FWD = false>
 __device__ __forceinline__ void chain_round_skew(ChainState<CPL>& cs, const float g, const float* e0, const float* s0,
                                                  float* st0, const int ex, const int lane, H1 h1, H2 h2,
                                                  const float* e1 = nullptr, const float* s1 = nullptr,
                                                  float* st1 = nullptr) {
     constexpr int max_u = 32 * CPL, SU = max_u + 32;
-    constexpr int istr = RANK == 0 ? max_u : -max_u;
+    constexpr int istr = (RANK == 0 || FWD) ? max_u : -max_u;
     constexpr int sstr = TO_SMEM ? max_u : (RANK == 0 ? SU : -SU);
     constexpr int CH = CPL <= 4 ? 4 : 2;  // rows per chunk (register budget)
     constexpr int NC = NR / CH;

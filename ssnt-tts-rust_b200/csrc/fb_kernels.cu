@@ -13,7 +13,7 @@
 //  * kind 0  fb_generic_kernel        any shape/alignment (max_u % 4 != 0, U > 1024, unaligned
 //            bases): one CTA per utterance, one thread per token, rows in shared memory, log2
 //            domain with one integer offset per token.
-#include "fb_bf.cuh"
+#include "fb_split.cuh"
 
 namespace ssnt {
 namespace {
@@ -97,6 +97,72 @@ __global__ void __launch_bounds__(kBfThreads, 1) fb_bf_kernel(const BfParams p) 
         }
     }
     if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kBfThreads);
+}
+
+
+template <int CPL>
+__global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();  // 0/1 recursion CTAs (alpha/beta), 2/3 their helper CTAs
+    const int b = blockIdx.x >> 2;
+    const FbArgs& a = p.a;
+    int T = a.t_len ? a.t_len[b] : a.max_t;
+    int U = a.u_len ? a.u_len[b] : a.max_u;
+    T = min(max(T, 0), a.max_t);
+    U = min(max(U, 0), a.max_u);
+    const size_t slab = (size_t)a.max_t * a.max_u;
+    if (T <= 0 || U <= 0 || U > T) {
+        // No monotonic path: ll = -inf, every gradient 0.  Uniform for the four CTAs of the cluster.
+        if (rank >= 2) {
+            float4* g = reinterpret_cast<float4*>((rank == 2 ? a.grad_emit : a.grad_shift) + (size_t)b * slab);
+            for (size_t i = tid; i < slab / 4; i += kSplitThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (rank == 0 && tid == 0) a.log_likelihood[b] = -INFINITY;
+    } else {
+        for (int i = tid; i < (kSplitHeaderBytes - 128) / 4; i += kSplitThreads) reinterpret_cast<int*>(smem_raw + 128)[i] = 0;
+        if (tid == 0) {
+            if (rank < 2) {
+                for (int s = 0; s < p.NS; ++s) mbar_init(smem_u32(reinterpret_cast<uint64_t*>(smem_raw) + s), 1);
+                fence_mbar_init();
+            }
+            if (rank == 0) p.status[b] = p.force_fallback ? (unsigned)kBfForced : 0u;
+        }
+        __syncthreads();
+        cluster.sync();  // flags are zero everywhere before anybody writes into a neighbour's shared memory
+        if (rank < 2) split_chain_cta<CPL>(p, b, rank, T, U, smem_raw);
+        else split_helper_cta<CPL>(p, b, rank, T, U, smem_raw);
+        // Padded frames t >= T (helper 0 clears grad_emit, helper 1 grad_shift).
+        if (rank >= 2) {
+            float4* g = reinterpret_cast<float4*>((rank == 2 ? a.grad_emit : a.grad_shift) + (size_t)b * slab +
+                                                  (size_t)T * a.max_u);
+            const size_t n4 = (size_t)(a.max_t - T) * a.max_u / 4;
+            for (size_t i = tid; i < n4; i += kSplitThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        // Did a helper flag the utterance?  If so the recursion CTAs redo it in the log domain.
+        __threadfence();
+        cluster.sync();
+        const unsigned st = *reinterpret_cast<volatile unsigned*>(p.status + b);
+        if (st) {
+            if (rank == 0 && tid == 0) atomicAdd(p.fallbacks, 1u);
+            if (rank < 2 && warp == 0) {
+                LogParams lp;
+                lp.a = a;
+                // this utterance's own A region doubles as the re-run's scratch rows
+                float* mine = p.A + (size_t)b * 2 * p.nstp * kG * p.SU;
+                lp.scratch = mine - (size_t)b * (a.max_t + 1) * p.SU;
+                lp.SU = p.SU;
+                lp.NS = p.NS < 8 ? p.NS : 8;
+                lp.counter = p.counter;
+                log_lattice_cta<CPL>(lp, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw + 512),
+                                     reinterpret_cast<float*>(smem_raw + kSplitHeaderBytes), cluster);
+            } else {
+                cluster.sync();
+            }
+        }
+    }
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kSplitThreads);
 }
 
 // ===============================================================================================
@@ -255,9 +321,43 @@ void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
     SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_bf_kernel<CPL>, p));
 }
 
+template <int CPL>
+void launch_split(const SplitParams& p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(fb_split_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)p.a.batch_size * 4u);
+    cfg.blockDim = dim3(kSplitThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_split_kernel<CPL>, p));
+}
+
 inline int round_up4(int x) { return (x + 3) & ~3; }
 
 }  // namespace
+
+// Split kernel (kind 4): probability rings P [B][2][ring][16*max_u], state rows A [B][2][nstp*8][SU], status [B].
+constexpr int kSplitRing = 32;  // stages of 8 rows; multiple of 16 (ring slots are owned by helper warp k % 16)
+static size_t split_workspace_bytes(int B, int max_t, int max_u) {
+    if (max_u != 64 && max_u != 128 && max_u != 256) return 0;
+    const size_t SU = (size_t)max_u + 32;
+    const size_t nstp = ((size_t)max_t + kG - 1) / kG;
+    const size_t ring = nstp < (size_t)kSplitRing ? ((nstp + 15) & ~(size_t)15) : (size_t)kSplitRing;
+    const size_t P = (size_t)B * 2 * ring * 2 * kG * max_u * sizeof(float);
+    const size_t A = (size_t)B * 2 * nstp * kG * SU * sizeof(float);
+    return P + A + (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255) + 512;
+}
 
 // Workspace: scratch rows (+1 virtual row, stride max_u+4 rounded to 4) and per-row offsets for
 // the generic kernel; sized for whichever kernel is picked.
@@ -267,6 +367,8 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     size_t warp_bytes = (size_t)B * (max_t + 1) * SU * sizeof(float) + (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
     size_t gen_bytes = (size_t)2 * B * max_t * max_u * sizeof(float);
     size_t n = warp_bytes > gen_bytes ? warp_bytes : gen_bytes;
+    const size_t split_bytes = split_workspace_bytes(B, max_t, max_u);
+    n = n > split_bytes ? n : split_bytes;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -302,11 +404,43 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
                    aligned16(a.log_shift) && aligned16(a.grad_emit) && aligned16(a.grad_shift) &&
                    aligned16(ws);
     const bool bf_ok = warp_ok && a.max_u <= 256;
+    const bool split_ok = bf_ok && (a.max_u == 64 || a.max_u == 128 || a.max_u == 256);
     int kind = tls_force_kind;
-    if (kind < 0) kind = bf_ok ? 2 : (warp_ok ? 1 : 0);
+    // few utterances (one wave of 4-CTA clusters): the split-role kernel keeps the recursion SMs free of
+    // everything else; many utterances: the fused kernel needs half the SMs per utterance
+    if (kind < 0) kind = (split_ok && a.batch_size * 4 <= sm_count() - 16) ? 4 : bf_ok ? 2 : (warp_ok ? 1 : 0);
+    if (kind >= 4) SSNT_ASSERT(split_ok, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");
     tls_last_kind = kind;
+
+    if (kind >= 4) {
+        SplitParams p;
+        p.a = a;
+        p.SU = a.max_u + 32;
+        p.nstp = (a.max_t + kG - 1) / kG;
+        p.ring = p.nstp < kSplitRing ? ((p.nstp + 15) & ~15) : kSplitRing;
+        const size_t Pf = (size_t)a.batch_size * 2 * p.ring * 2 * kG * a.max_u;
+        const size_t Af = (size_t)a.batch_size * 2 * p.nstp * kG * p.SU;
+        p.P = (float*)ws;
+        p.A = p.P + Pf;
+        p.log_scratch = nullptr;
+        p.status = (unsigned*)(p.A + Af);
+        p.fallbacks = device_fallback_counter();
+        p.force_fallback = kind == 5 ? 1 : 0;  // kind 5: run the split kernel but force the log-domain re-run
+        p.counter = counter;
+        p.stats = tls_stats;
+        const size_t slot_bytes = ((size_t)3 * kG * a.max_u + 32) * sizeof(float);
+        int NS = (int)((size_t)(224 * 1024 - kSplitHeaderBytes) / slot_bytes);
+        NS = NS > 16 ? 16 : NS;
+        SSNT_ASSERT(NS >= 4, "forward_backward: ring does not fit shared memory");
+        p.NS = NS;
+        const size_t smem = kSplitHeaderBytes + (size_t)NS * slot_bytes;
+        if (a.max_u == 64) launch_split<2>(p, smem, stream);
+        else if (a.max_u == 128) launch_split<4>(p, smem, stream);
+        else launch_split<8>(p, smem, stream);
+        return;
+    }
 
     if (kind >= 2) {
         BfParams p;
