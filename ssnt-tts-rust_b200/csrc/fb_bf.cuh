@@ -524,13 +524,17 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
                 fence_proxy_async();
             }
             const Phase& P = ph[phase];
-            // Four stages are issued per round: lane l handles array (l % 3) of stage (l / 3) of the
+            // Up to four stages are issued per round: lane l handles array (l % 3) of stage (l / 3) of the
             // batch, so one cp.async.bulk instruction starts up to 12 copies (the issue cost is per
             // instruction, ~150-300 cycles, not per copy).  Lanes 12-13 issue the L2 prefetches.  No
             // proxy fence per stage: a slot is only refilled after the helpers that read it last
             // published `done`, and a fence.proxy.async here would wait for the copies still in
             // flight, collapsing the ring to a single outstanding stage.
-            constexpr int NB = 4;
+            // The batch must stay shallow relative to the ring: a helper pair frees the slot of stage y
+            // (post) only after it prepared stage y+3, so a batch that waits for the slots of k0-NS ..
+            // k0+NB-1-NS needs the copies of stage k0+NB+2-NS to have been issued by an EARLIER batch:
+            // NS > NB + 2 + (NB - 1) (shallow rings: max_u > 128).  A deeper batch dead-locks.
+            const int NB = NS >= 10 ? 4 : (NS >= 6 ? 2 : 1);
             const int jb = lane / 3, arr = lane - jb * 3;
             const int narr = P.with_x ? 3 : 2;
             for (int k0 = 0; k0 < P.nst; k0 += NB) {

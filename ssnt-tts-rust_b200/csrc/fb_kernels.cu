@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
     const unsigned rank = cluster.block_rank();  // 0/1 recursion CTAs (alpha/beta), 2/3 their helper CTAs
     const int b = blockIdx.x >> 2;
     const FbArgs& a = p.a;
+    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; };
+    long long* tl = p.stats ? p.stats + (size_t)gridDim.x * 16 * 16 + (size_t)blockIdx.x * 4 : nullptr;  // launch timeline (ns)
+    if (tl && tid == 0) tl[0] = gtime();
     int T = a.t_len ? a.t_len[b] : a.max_t;
     int U = a.u_len ? a.u_len[b] : a.max_u;
     T = min(max(T, 0), a.max_t);
@@ -123,14 +126,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
     } else {
         for (int i = tid; i < (kSplitHeaderBytes - 128) / 4; i += kSplitThreads) reinterpret_cast<int*>(smem_raw + 128)[i] = 0;
         if (tid == 0) {
-            if (rank < 2) {
-                for (int s = 0; s < p.NS; ++s) mbar_init(smem_u32(reinterpret_cast<uint64_t*>(smem_raw) + s), 1);
-                fence_mbar_init();
-            }
             if (rank == 0) p.status[b] = p.force_fallback ? (unsigned)kBfForced : 0u;
         }
         __syncthreads();
         cluster.sync();  // flags are zero everywhere before anybody writes into a neighbour's shared memory
+        if (tl && tid == 0) tl[1] = gtime();
         if (rank < 2) split_chain_cta<CPL>(p, b, rank, T, U, smem_raw);
         else split_helper_cta<CPL>(p, b, rank, T, U, smem_raw);
         // Padded frames t >= T (helper 0 clears grad_emit, helper 1 grad_shift).
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
             for (size_t i = tid; i < n4; i += kSplitThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
         }
         // Did a helper flag the utterance?  If so the recursion CTAs redo it in the log domain.
+        if (tl && tid == 0) tl[2] = gtime();
         __threadfence();
         cluster.sync();
         const unsigned st = *reinterpret_cast<volatile unsigned*>(p.status + b);
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
         }
     }
     if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kSplitThreads);
+    if (tl && tid == 0) tl[3] = gtime();
 }
 
 // ===============================================================================================
@@ -347,16 +349,13 @@ inline int round_up4(int x) { return (x + 3) & ~3; }
 
 }  // namespace
 
-// Split kernel (kind 4): probability rings P [B][2][ring][16*max_u], state rows A [B][2][nstp*8][SU], status [B].
-constexpr int kSplitRing = 32;  // stages of 8 rows; multiple of 16 (ring slots are owned by helper warp k % 16)
+// Split kernel (kind 4): state rows A [B][2][nstp*8][SU] (both sweeps, sweep order) and status [B].
 static size_t split_workspace_bytes(int B, int max_t, int max_u) {
     if (max_u != 64 && max_u != 128 && max_u != 256) return 0;
     const size_t SU = (size_t)max_u + 32;
     const size_t nstp = ((size_t)max_t + kG - 1) / kG;
-    const size_t ring = nstp < (size_t)kSplitRing ? ((nstp + 15) & ~(size_t)15) : (size_t)kSplitRing;
-    const size_t P = (size_t)B * 2 * ring * 2 * kG * max_u * sizeof(float);
     const size_t A = (size_t)B * 2 * nstp * kG * SU * sizeof(float);
-    return P + A + (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255) + 512;
+    return A + (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255) + 512;
 }
 
 // Workspace: scratch rows (+1 virtual row, stride max_u+4 rounded to 4) and per-row offsets for
@@ -419,12 +418,8 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         p.a = a;
         p.SU = a.max_u + 32;
         p.nstp = (a.max_t + kG - 1) / kG;
-        p.ring = p.nstp < kSplitRing ? ((p.nstp + 15) & ~15) : kSplitRing;
-        const size_t Pf = (size_t)a.batch_size * 2 * p.ring * 2 * kG * a.max_u;
         const size_t Af = (size_t)a.batch_size * 2 * p.nstp * kG * p.SU;
-        p.P = (float*)ws;
-        p.A = p.P + Pf;
-        p.log_scratch = nullptr;
+        p.A = (float*)ws;
         p.status = (unsigned*)(p.A + Af);
         p.fallbacks = device_fallback_counter();
         p.force_fallback = kind == 5 ? 1 : 0;  // kind 5: run the split kernel but force the log-domain re-run

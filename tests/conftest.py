@@ -32,6 +32,7 @@ def load_product():
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (B200); run via gpurun")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout) for kernels that could hang")
 
 
 def has_cuda() -> bool:

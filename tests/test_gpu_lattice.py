@@ -108,7 +108,9 @@ def test_infeasible_empty_and_masked(product, oracle_mod):
     le[0, 3, 2] = -np.inf                            # a single forbidden cell is fine
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     assert np.isneginf(want[0][[1, 2, 3, 5]]).all() and np.isfinite(want[0][[0, 4]]).all()
-    for kind in (0, 1, 2, 3):
+    for kind in (0, 1, 2, 3, 4, 5):
+        if kind >= 4:
+            continue  # max_u = 8 here; the split-role kernel needs max_u in {64, 128, 256} (covered below)
         got, _ = _run(product, le, ls, t_len, u_len, "device", kind)
         _check(got, want, t_len, u_len)
         assert np.isposinf(_np(got[1])[0])
@@ -120,7 +122,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     le, ls = make_inputs(32, 800, 128, seed=1234)
     want = oracle_mod.forward_backward(le, ls)
     got, used = _run(product, le, ls, None, None, space)
-    assert used == 2
+    assert used == 4  # B=32: the split-role block-float kernel (one cluster of four CTAs per utterance)
     _check(got, want)
     ll, loss, ge, gs = (_np(g) for g in got)
     rows = (ge + gs).sum(axis=2)
@@ -128,7 +130,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)  # exactly U-1 shifts
 
 
-@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("kind", [1, 2, 4])
 def test_config2_ragged(product, oracle_mod, kind):
     le, ls = make_inputs(32, 800, 128, seed=77)
     t_len, u_len = ragged_lengths(32, 800, 128)
@@ -161,7 +163,7 @@ def test_peaked_and_uniform_inputs(product, oracle_mod):
     le[2], ls[2] = np.log(1e-10), np.log1p(-1e-10)        # model insists on shifting every frame
     le[3], ls[3] = np.log1p(-1e-6), np.log(1e-6)          # model never wants to shift
     want = oracle_mod.forward_backward(le, ls)
-    for kind in (0, 1, 2):   # kind 2 must notice what it cannot hold and re-run it in the log domain
+    for kind in (0, 1, 2, 4):   # kinds 2 and 4 must notice what they cannot hold and re-run it in the log domain
         got, _ = _run(product, le, ls, None, None, "device", kind)
         _check(got, want)
 
@@ -260,3 +262,53 @@ def test_tone_latent_infeasible(product, oracle_mod):
     got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
     _check_tone(got, want)
     assert np.isneginf(_np(got[0])[:2]).all()
+
+
+# ---- split-role kernel (kind 4; kind 5 = 4 with the log-domain re-run forced) and wide lattices ----------------
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("kind", [2, 3, 4, 5])
+@pytest.mark.parametrize("B,T,U", [(3, 64, 64), (2, 9, 64), (5, 333, 128), (2, 801, 128), (3, 130, 128),
+                                   (2, 700, 256), (1, 300, 256), (35, 200, 128)])
+def test_full_width_lattices_all_block_float_kernels(product, oracle_mod, kind, B, T, U):
+    """max_u in {64, 128, 256}: the shapes the split-role kernel takes, ragged lengths, including
+    U=256 (shallow shared-memory ring — a producer batch deeper than the ring once dead-locked the
+    fused kernel here) and U close to T (steep fronts: the block-float kernels must fall back)."""
+    le, ls = make_inputs(B, T, U, seed=T * 7 + U + kind)
+    rng = np.random.default_rng(T + U)
+    t_len = rng.integers(max(1, T // 2), T + 1, B).astype(np.int32)
+    u_len = np.array([rng.integers(1, min(U, tb) + 1) for tb in t_len], np.int32)
+    t_len[0] = T
+    u_len[0] = min(U, T)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, used = _run(product, le, ls, t_len, u_len, "device", kind)
+    assert used == kind
+    _check(got, want, t_len, u_len)
+
+
+@pytest.mark.timeout(120)
+def test_split_kernel_infeasible_and_masked(product, oracle_mod):
+    le, ls = make_inputs(6, 80, 64, seed=15)
+    t_len = np.array([80, 0, 30, 80, 1, 80], np.int32)
+    u_len = np.array([64, 2, 50, 0, 1, 64], np.int32)   # 1: T=0, 2: U>T, 3: U=0 → ll=-inf, grads 0
+    le[5, 40, :] = -np.inf
+    ls[5, 40, :] = -np.inf                                 # no path at all → -inf
+    le[0, 3, 2] = -np.inf
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    for kind in (2, 4, 5):
+        got, used = _run(product, le, ls, t_len, u_len, "device", kind)
+        assert used == kind
+        _check(got, want, t_len, u_len)
+
+
+@pytest.mark.timeout(120)
+def test_auto_dispatch_small_and_large_batches(product):
+    """Few utterances → split-role kernel (kind 4); more than one wave of 4-CTA clusters → fused kernel."""
+    import torch
+    for B, want_kind in ((4, 4), (32, 4), (64, 2)):
+        z = torch.randn(B, 200, 128, device="cuda")
+        le, ls = torch.nn.functional.logsigmoid(z), torch.nn.functional.logsigmoid(-z)
+        ll, loss, ge, gs = product.forward_backward(le, ls)
+        torch.cuda.synchronize()
+        assert product.fb_kernel_used() == want_kind
+        rows = (ge + gs).sum(dim=2)
+        assert torch.allclose(rows, torch.ones_like(rows), atol=2e-4)
