@@ -68,15 +68,22 @@ private:
     std::vector<Out> outs_;
 };
 
-// Streams used to overlap H2D / kernel / D2H of batch chunks in the host-pointer lattice call.
+// Streams used to overlap H2D / kernel / D2H of batch chunks in the host-pointer lattice call: one
+// stream per copy direction (each keeps its DMA engine busy back to back) and a few compute streams
+// (the kernels of small chunks are latency-bound and overlap each other).
+constexpr int kMaxChunks = 8;
+constexpr int kComputeStreams = 4;
 struct AuxStreams {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    cudaStream_t h2d = nullptr, d2h = nullptr, k[kComputeStreams] = {};
+    cudaEvent_t start = nullptr, in_done[kMaxChunks] = {}, k_done[kMaxChunks] = {};
     void init() {
-        if (s[0]) return;
-        for (int i = 0; i < 2; ++i) {
-            SSNT_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
-            SSNT_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        if (h2d) return;
+        SSNT_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        SSNT_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < kComputeStreams; ++i) SSNT_CUDA(cudaStreamCreateWithFlags(&k[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) {
+            SSNT_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+            SSNT_CUDA(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
         }
         SSNT_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     }
@@ -265,8 +272,11 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
         launch_forward_backward(a, current_stream());
         return;
     }
-    // Host buffers: split the batch into chunks and run H2D(k+1) | kernel(k) | D2H(k-1) on two
-    // auxiliary streams so the PCIe link is busy in both directions.
+    // Host buffers: split the batch into chunks, one stream per chunk (H2D, kernel, D2H in stream
+    // order).  The copy engines serve the streams in issue order, so chunk c+1 uploads while chunk c
+    // computes and chunk c-1 downloads: the PCIe link is busy in both directions.  Few API calls per
+    // chunk matter as much as the overlap: the host thread's issue time (~5 us per call) is on the
+    // critical path of a ~0.7 ms call, hence no events and one download of the likelihoods at the end.
     const size_t slab = n2(max_t, max_u);
     const int B = batch_size > 0 ? batch_size : 0;
     float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
@@ -277,10 +287,13 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
     int* d_tl = (int*)device_scratch(9, (size_t)B * sizeof(int) + 16);
     int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
     int nchunks = 1;
-    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 8 ? 4 : 2;
+    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 8 ? kComputeStreams : 2;
+    if (const char* e = std::getenv("SSNT_FB_CHUNKS")) {  // tuning aid
+        nchunks = std::atoi(e);
+        nchunks = nchunks < 1 ? 1 : (nchunks > kMaxChunks ? kMaxChunks : nchunks);
+        if (nchunks > B) nchunks = B > 0 ? B : 1;
+    }
     const int per = (B + nchunks - 1) / (nchunks > 0 ? nchunks : 1);
-    float* d_loss = (float*)device_scratch(11, 8 * sizeof(float));
-    float* h_loss = (float*)pinned_scratch(0, 8 * sizeof(float));
     const size_t ws_each = fb_workspace_bytes(per, max_t, max_u);
     char* ws = (char*)device_scratch(0, ws_each * nchunks);
     tls_aux.init();
@@ -290,26 +303,26 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
         if (nb <= 0) break;
-        cudaStream_t s = tls_aux.s[c & 1];
-        if (c < 2) SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
+        cudaStream_t s = tls_aux.k[c % kComputeStreams];
+        if (c < kComputeStreams) SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
         const size_t o = (size_t)b0 * slab, nbytes = (size_t)nb * slab * sizeof(float);
         SSNT_CUDA(cudaMemcpyAsync(d_le + o, log_emit + o, nbytes, cudaMemcpyHostToDevice, s));
         SSNT_CUDA(cudaMemcpyAsync(d_ls + o, log_shift + o, nbytes, cudaMemcpyHostToDevice, s));
         if (t_len) SSNT_CUDA(cudaMemcpyAsync(d_tl + b0, t_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
         if (u_len) SSNT_CUDA(cudaMemcpyAsync(d_ul + b0, u_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
         FbArgs a{d_le + o, d_ls + o, t_len ? d_tl + b0 : nullptr, u_len ? d_ul + b0 : nullptr, nb, max_t,
-                 max_u, d_ll + b0, d_loss + c, d_ge + o, d_gs + o, ws + (size_t)c * ws_each, ws_each};
+                 max_u, d_ll + b0, nullptr, d_ge + o, d_gs + o, ws + (size_t)c * ws_each, ws_each};
         launch_forward_backward(a, s);
         SSNT_CUDA(cudaMemcpyAsync(grad_emit + o, d_ge + o, nbytes, cudaMemcpyDeviceToHost, s));
         SSNT_CUDA(cudaMemcpyAsync(grad_shift + o, d_gs + o, nbytes, cudaMemcpyDeviceToHost, s));
-        SSNT_CUDA(cudaMemcpyAsync(log_likelihood + b0, d_ll + b0, nb * sizeof(float), cudaMemcpyDeviceToHost, s));
-        SSNT_CUDA(cudaMemcpyAsync(h_loss + c, d_loss + c, sizeof(float), cudaMemcpyDeviceToHost, s));
         used = c + 1;
     }
-    for (int i = 0; i < 2 && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.s[i]));
+    for (int i = 0; i < kComputeStreams && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.k[i]));
+    if (B > 0) SSNT_CUDA(cudaMemcpy(log_likelihood, d_ll, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost));
     if (loss) {
+        // loss = -sum_b ll[b] in batch order, in double (what the kernel's own reduction computes)
         double acc = 0.0;
-        for (int c = 0; c < used; ++c) acc += (double)h_loss[c];
+        for (int b2 = 0; b2 < B; ++b2) acc -= (double)log_likelihood[b2];
         *loss = (float)acc;
     }
 }

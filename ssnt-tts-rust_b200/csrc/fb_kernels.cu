@@ -423,6 +423,8 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         p.status = (unsigned*)(p.A + Af);
         p.fallbacks = device_fallback_counter();
         p.force_fallback = kind == 5 ? 1 : 0;  // kind 5: run the split kernel but force the log-domain re-run
+        p.debug = 0;
+        if (const char* e = std::getenv("SSNT_SPLIT_DEBUG")) p.debug = std::atoi(e);  // profiling aid
         p.counter = counter;
         p.stats = tls_stats;
         const size_t slot_bytes = ((size_t)3 * kG * a.max_u + 32) * sizeof(float);

@@ -44,6 +44,7 @@ struct SplitParams {
     unsigned* fallbacks;
     int SU, NS, nstp;
     int force_fallback;
+    int debug;         // profiling aid (SSNT_SPLIT_DEBUG): 1 skip re-normalisation, 2 skip decision hooks (results wrong)
     unsigned* counter;
     long long* stats;
 };
@@ -231,13 +232,13 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
             float* sp[4];
 #pragma unroll
             for (int z = 0; z < 4; ++z) sp[z] = slot_ptr(sl[z]);
-            apply_decision();
+            if (!(p.debug & 1)) apply_decision();
 #pragma unroll
             for (int z = 0; z < 4; ++z)
                 if (z < ns) reinterpret_cast<int*>(sp[z] + stageP + kG * max_u)[lane] = ex;
             int own = kNoMass, nbmag = kNoMass;
-            auto d1 = [&]() { decide_1(own, nbmag); };
-            auto d2 = [&]() { decide_2(own, nbmag); };
+            auto d1 = [&]() { if (!(p.debug & 2)) decide_1(own, nbmag); };
+            auto d2 = [&]() { if (!(p.debug & 2)) decide_2(own, nbmag); };
             const long long tr1 = p.stats ? clock64() : 0;
             st_mid += tr1 - tm0;
             if (d == 0) {
