@@ -238,15 +238,27 @@ def run_b200(args):
         sets.append((le, ls, ws, out))
     torch.cuda.synchronize()
 
+    pending = []
+
     def step(i):
         le, ls, ws, out = sets[i % nsets]
         ll, loss, ge, gs = P.forward_backward(le, ls, workspace=ws, out=out)
         if world > 1:
-            dist.all_reduce(loss)  # the path's only collective: 4 bytes
+            # the path's only collective: 4 bytes.  Issued asynchronously (NCCL's stream waits for this
+            # step's kernel; the next step's kernel does not wait for the all-reduce), completed by
+            # drain() inside the timed region.
+            pending.append(dist.all_reduce(loss, async_op=True))
+            if len(pending) > 64:
+                pending.pop(0).wait()
         return loss
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     for i in range(max(args.warmup, 3)):
         step(i)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -256,6 +268,7 @@ def run_b200(args):
         ev0.record()
         for i in range(args.steps):
             loss = step(i)
+        drain()
         ev1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -263,10 +276,13 @@ def run_b200(args):
         torch.cuda.synchronize()
         # keep sampling a little under load if the run was very short
         if args.steps * 1e-4 < 0.3:
+            # local compute only: a time-bounded loop must not contain collectives (ranks would issue
+            # different numbers of them and dead-lock)
             t_end = time.perf_counter() + 0.4
             i = 0
             while time.perf_counter() < t_end:
-                step(i)
+                le, ls, ws, out = sets[i % nsets]
+                P.forward_backward(le, ls, workspace=ws, out=out)
                 i += 1
             torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
