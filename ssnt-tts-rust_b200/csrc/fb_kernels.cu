@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
                 float* mine = p.A + (size_t)b * 2 * p.nstp * kG * p.SU;
                 lp.scratch = mine - (size_t)b * (a.max_t + 1) * p.SU;
                 lp.SU = p.SU;
-                lp.NS = p.NS < 8 ? p.NS : 8;
+                {
+                    const int log_stage_bytes = kG * (2 * a.max_u + p.SU) * (int)sizeof(float);
+                    const int fit = p.ring_bytes / log_stage_bytes;
+                    lp.NS = fit < 8 ? fit : 8;  // >= 2: a split slot is 3 rows wide per row, a log stage 3.1
+                }
                 lp.counter = p.counter;
                 log_lattice_cta<CPL>(lp, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw + 512),
                                      reinterpret_cast<float*>(smem_raw + kSplitHeaderBytes), cluster);
@@ -429,9 +433,10 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         p.stats = tls_stats;
         const size_t slot_bytes = ((size_t)3 * kG * a.max_u + 32) * sizeof(float);
         int NS = (int)((size_t)(224 * 1024 - kSplitHeaderBytes) / slot_bytes);
-        NS = NS > 16 ? 16 : NS;
-        SSNT_ASSERT(NS >= 4, "forward_backward: ring does not fit shared memory");
+        NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);  // power of two (the recursion indexes the ring with masks)
+        SSNT_ASSERT((size_t)NS * slot_bytes + kSplitHeaderBytes <= 224 * 1024, "forward_backward: ring does not fit shared memory");
         p.NS = NS;
+        p.ring_bytes = (int)((size_t)NS * slot_bytes);
         const size_t smem = kSplitHeaderBytes + (size_t)NS * slot_bytes;
         if (a.max_u == 64) launch_split<2>(p, smem, stream);
         else if (a.max_u == 128) launch_split<4>(p, smem, stream);

@@ -43,6 +43,7 @@ struct SplitParams {
     unsigned* status;  // [B]
     unsigned* fallbacks;
     int SU, NS, nstp;
+    int ring_bytes;    // dynamic shared memory behind the header (sizes the log-domain re-run's own ring)
     int force_fallback;
     int debug;         // profiling aid (SSNT_SPLIT_DEBUG): 1 skip re-normalisation, 2 skip decision hooks (results wrong)
     unsigned* counter;
@@ -190,8 +191,10 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
             nbex_dec = d == 0 ? __shfl_up_sync(kFull, nw, 1) : __shfl_down_sync(kFull, nw, 1);
             have_dec = true;
         };
-        int slot = 0, use1 = 1;
-        int fl[4] = {0, 0, 0, 0};  // ready flags of this round's slots, loaded a round ahead
+        // NS is a power of two and a multiple of 4, rounds start at multiples of 4 stages: the four
+        // slots of a round are consecutive, share one use count, and their flags are one 16-byte word.
+        const int lgNS = NS == 16 ? 4 : (NS == 8 ? 3 : 2);
+        int4 fl = make_int4(0, 0, 0, 0);  // ready flags of this round's slots, loaded a round ahead
         const long long st_t0 = p.stats ? clock64() : 0;
         long long st_wait = 0, st_first = 0, st_rows = 0, st_hand = 0, st_mid = 0, st_warm = 0;
         // The first pass over the round body is a WARM-UP on whatever the ring holds: the recursion warp
@@ -201,37 +204,36 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
         const ChainState<CPL> cs0 = cs;
         for (int k = 0; k < nst;) {
             const int ns = nst - k >= 4 ? 4 : (nst - k >= 2 ? 2 : 1);  // stages of this round
-            int sl[4], us[4];
-            {
-                int s2 = slot, u2 = use1;
+            const int slot0 = k & (NS - 1);
+            const int use = (k >> lgNS) + 1;
+            const int* rflag = ready + (slot0 & ~3);  // aligned group of four flags that holds this round's
+            const int fo = slot0 & 3;                 // first flag of the round inside the group (0 or 2, tail only)
+            auto round_ready = [&](const int4& f) {
+                const int v[4] = {f.x, f.y, f.z, f.w};
+                bool ok = true;
 #pragma unroll
-                for (int z = 0; z < 4; ++z) {
-                    sl[z] = s2; us[z] = u2;
-                    if (++s2 == NS) { s2 = 0; ++u2; }
-                }
-            }
+                for (int z = 0; z < 4; ++z)
+                    if (z >= fo && z < fo + ns) ok = ok && v[z] >= use;
+                return ok;
+            };
             const long long tw0 = p.stats ? clock64() : 0;
-#pragma unroll
-            for (int z = 0; z < 4; ++z)
-                if (z < ns && !warmup)
-                    while (!__all_sync(kFull, fl[z] >= us[z])) fl[z] = flag_load(ready + sl[z]);
+            if (!warmup)
+                while (!__all_sync(kFull, round_ready(fl))) {
+                    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(rflag)) : "memory");
+                }
             const long long tm0 = p.stats ? clock64() : 0;
             if (p.stats) { st_wait += tm0 - tw0; if (k == 0) st_first = tm0 - st_t0; }
-            // request the flags of the next round's slots now; they are looked at a round later
-            int slot_n = slot, use_n = use1;
-            for (int z = 0; z < ns; ++z)
-                if (++slot_n == NS) { slot_n = 0; ++use_n; }
+            // request the flags of the next round's group now; they are looked at a round later
             {
-                int s2 = slot_n;
-#pragma unroll
-                for (int z = 0; z < 4; ++z) {
-                    fl[z] = flag_load(ready + s2);
-                    if (++s2 == NS) s2 = 0;
-                }
+                const int kn = k + ns;
+                const int* nflag = ready + ((kn & (NS - 1)) & ~3);
+                asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(nflag)) : "memory");
             }
             float* sp[4];
 #pragma unroll
-            for (int z = 0; z < 4; ++z) sp[z] = slot_ptr(sl[z]);
+            for (int z = 0; z < 4; ++z) sp[z] = slot_ptr((slot0 + z) & (NS - 1));
             if (!(p.debug & 1)) apply_decision();
 #pragma unroll
             for (int z = 0; z < 4; ++z)
@@ -256,24 +258,25 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
                 cs = cs0;
                 have_dec = false;
                 warmup = false;
-#pragma unroll
-                for (int z = 0; z < 4; ++z) fl[z] = 0;
+                fl = make_int4(0, 0, 0, 0);
                 continue;
             }
             st_rows += tr2 - tr1;
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
+                if (ns == 4) {
+                    asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %1, %1, %1};" ::"r"(smem_u32(state_done + slot0)), "r"(use) : "memory");
+                } else {
 #pragma unroll
-                for (int z = 0; z < 4; ++z)
-                    if (z < ns)
-                        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(state_done + sl[z])), "r"(us[z]) : "memory");
+                    for (int z = 0; z < 2; ++z)
+                        if (z < ns)
+                            asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(state_done + slot0 + z)), "r"(use) : "memory");
+                }
             }
             __syncwarp();
             if (p.stats) st_hand += clock64() - tr2;
             k += ns;
-            slot = slot_n;
-            use1 = use_n;
         }
         if (p.stats && lane == 0) {
             long long* o = p.stats + ((size_t)blockIdx.x * 16 + warp) * 16;
