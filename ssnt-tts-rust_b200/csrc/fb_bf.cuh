@@ -197,7 +197,9 @@ __device__ __forceinline__ void skew_step(ChainState<CPL>& cs, const float (&E)[
     if (RANK == 0) {
         float last_new;
         if (CPL > 2) last_new = fmaf(cs.a[L], E[L], cs.a[L - 1] * S[L - 1]);
-        const float a0n = fmaf(cs.a[0], cs.Ec, cs.inA * Qc);
+        // (inA, Qc, a0*Ec) and not (a0, Ec, inA*Qc): the product inA*Qc would be hoisted to right behind the
+        // shuffle that produces inA and stall on it; this form is tied to the lag cell's previous value
+        const float a0n = fmaf(cs.inA, Qc, cs.a[0] * cs.Ec);
         out[0] = a0n;
 #pragma unroll
         for (int i = 1; i < CPL; ++i) out[i] = cs.a[i];
@@ -215,7 +217,7 @@ __device__ __forceinline__ void skew_step(ChainState<CPL>& cs, const float (&E)[
     } else {
         float first_new;
         if (CPL > 2) first_new = fmaf(E[0], cs.a[0], S[0] * cs.a[1]);
-        const float aLn = fmaf(cs.a[L], cs.Ec, cs.inA * Qc);
+        const float aLn = fmaf(cs.inA, Qc, cs.a[L] * cs.Ec);
         out[L] = aLn;
 #pragma unroll
         for (int i = 0; i < L; ++i) out[i] = cs.a[i];
@@ -247,7 +249,7 @@ __device__ __forceinline__ void chain_round_skew(ChainState<CPL>& cs, const floa
     constexpr int max_u = 32 * CPL, SU = max_u + 32;
     constexpr int istr = (RANK == 0 || FWD) ? max_u : -max_u;
     constexpr int sstr = TO_SMEM ? max_u : (RANK == 0 ? SU : -SU);
-    constexpr int CH = CPL <= 4 ? 4 : 2;  // rows per chunk (register budget)
+    constexpr int CH = 4;  // rows per chunk (CPL = 8: 2 x 4 x 17 = 136 registers of operands, fine at 255)
     constexpr int NC = NR / CH;
     const int c0 = lane * CPL;
     const int pc = c0 > 0 ? c0 - 1 : 0;

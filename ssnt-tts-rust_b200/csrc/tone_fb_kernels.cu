@@ -53,6 +53,23 @@ __device__ float block_max(float v, float* red) {
     return r;
 }
 
+// ---- asynchronous row prefetch (cp.async) -------------------------------------------------------
+// The recursion is t-serial and every row needs 2·K fresh inputs per token (3·K in the backward
+// sweep, with the stored alpha row): read in the loop they put one global-memory latency (~1 us)
+// on the dependency chain of EVERY row.  Instead each thread copies its own tokens' values of the
+// row kPF steps ahead into a shared-memory ring with cp.async and reads back only what it wrote
+// itself, so no barrier is involved — only cp.async.wait_group.
+constexpr int kPF = 8;  // rows in flight
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pf() { asm volatile("cp.async.wait_group %0;" ::"n"(kPF) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct ToneParams {
     ToneFbArgs a;
     float* scratch;  // [B][T][U][K] alpha~
@@ -60,13 +77,17 @@ struct ToneParams {
     unsigned* counter;
 };
 
+// KT > 0: tone_class_size known at compile time (the loops over the tones unroll and their
+// shared-memory loads batch); KT == 0: any K.
+template <int KT>
 __global__ void tone_fb_kernel(const ToneParams p) {
     extern __shared__ float sm[];
     __shared__ float red[32];
     __shared__ unsigned s_last;
     const ToneFbArgs& a = p.a;
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int max_t = a.max_t, max_u = a.max_u, K = a.tone_class_size;
+    const int max_t = a.max_t, max_u = a.max_u;
+    const int K = KT > 0 ? KT : a.tone_class_size;
     int T = a.t_len ? a.t_len[b] : max_t;
     int U = a.u_len ? a.u_len[b] : max_u;
     T = min(max(T, 0), max_t);
@@ -96,6 +117,39 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         float* srow = nxt + RW;           // S(t,u) or Bm(t+1,u), index u+1
         float* tone2 = srow + (max_u + 2);
         float* gacc = tone2 + max_u * K;
+        // [kPF + 1][3][max_u * K]: le | ls | stored alpha of a row; 16-byte aligned for cp.async
+        float* soffs = gacc + max_u * K;  // [max_t] integer row offsets of the stored alpha rows
+        float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(soffs + max_t) + 15) & ~(uintptr_t)15);
+        const int RS = 3 * max_u * K;
+        const bool vec16 = (K % 4 == 0) && ((max_u * K) % 4 == 0) && ((reinterpret_cast<uintptr_t>(le) | reinterpret_cast<uintptr_t>(ls) |
+                                             reinterpret_cast<uintptr_t>(scr)) % 16 == 0);
+        // copies this thread's tokens of row t (le, ls and, when with_alpha, the stored alpha row) into
+        // ring slot t % (kPF+1); always commits a group (possibly empty) so that group counts line up
+        auto issue_row = [&](int t, bool with_alpha) {
+            if (t >= 0 && t < T) {
+                float* dst = ring + (size_t)(t % (kPF + 1)) * RS;
+                const size_t ro = (size_t)t * max_u * K;
+                for (int u = tid; u < U; u += nt) {
+                    const int o = u * K;
+                    if (vec16) {
+#pragma unroll
+                        for (int k = 0; k < K; k += 4) {
+                            cp_async16(dst + o + k, le + ro + o + k);
+                            cp_async16(dst + max_u * K + o + k, ls + ro + o + k);
+                            if (with_alpha) cp_async16(dst + 2 * max_u * K + o + k, scr + ro + o + k);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            cp_async4(dst + o + k, le + ro + o + k);
+                            cp_async4(dst + max_u * K + o + k, ls + ro + o + k);
+                            if (with_alpha) cp_async4(dst + 2 * max_u * K + o + k, scr + ro + o + k);
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
         for (int i = tid; i < RW; i += nt) { cur[i] = kNeg; nxt[i] = kNeg; }
         for (int i = tid; i < max_u + 2; i += nt) srow[i] = kNeg;
         for (int i = tid; i < max_u * K; i += nt) {
@@ -107,7 +161,12 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         __syncthreads();
         float off = 0.0f;
         // ------------------------------ forward ------------------------------
+        for (int t = 0; t < kPF; ++t) issue_row(t, false);
         for (int t = 0; t < T; ++t) {
+            issue_row(t + kPF, false);
+            cp_async_wait_pf();  // row t has landed (this thread's part, which is all it reads)
+            const float* rle = ring + (size_t)(t % (kPF + 1)) * RS;
+            const float* rls = rle + max_u * K;
             if ((t & 15) == 15) {
                 float mx = kNeg;
                 for (int i = tid; i < U * K; i += nt) mx = fmaxf(mx, cur[K + i]);
@@ -118,19 +177,30 @@ __global__ void tone_fb_kernel(const ToneParams p) {
                 __syncthreads();
             }
             for (int i = tid; i < U * K; i += nt) scr[(size_t)t * max_u * K + i] = cur[K + i];
-            if (tid == 0) offs[t] = off;
+            if (tid == 0) soffs[t] = off;
             if (t < T - 1) {
                 for (int u = tid; u < U; u += nt) {
+                    // LSE over the K tones as max + one LG2 of a sum of EX2s: the K exponentials are
+                    // independent (a chain of K pairwise log-add-exps costs K dependent EX2+LG2 pairs)
                     float acc = kNeg;
-                    if (u < U - 1)
-                        for (int k = 0; k < K; ++k)
-                            acc = lae2(acc, cur[(u + 1) * K + k] + to_log2(ls[((size_t)t * max_u + u) * K + k]));
+                    if (u < U - 1) {
+                        float mx = kNeg;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) mx = fmaxf(mx, cur[(u + 1) * K + k] + to_log2(rls[u * K + k]));
+                        if (mx > kNegTest) {
+                            float sum = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) sum += ex2((cur[(u + 1) * K + k] + to_log2(rls[u * K + k])) - mx);
+                            acc = mx + lg2(sum);
+                        }
+                    }
                     srow[u + 1] = acc;
                 }
                 __syncthreads();
                 for (int u = tid; u < U; u += nt)
+#pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const float stay = cur[(u + 1) * K + k] + to_log2(le[((size_t)t * max_u + u) * K + k]);
+                        const float stay = cur[(u + 1) * K + k] + to_log2(rle[u * K + k]);
                         const float sh = u > 0 ? tone2[u * K + k] + srow[u] : kNeg;
                         nxt[(u + 1) * K + k] = lae2(stay, sh);
                     }
@@ -138,9 +208,12 @@ __global__ void tone_fb_kernel(const ToneParams p) {
                 float* tmp = cur; cur = nxt; nxt = tmp;
             }
         }
-        __syncthreads();
+        cp_async_wait_all();
+        __syncthreads();  // also: every stored alpha row is written before the backward sweep prefetches it
+        __threadfence_block();
         {
             float acc = kNeg;
+#pragma unroll
             for (int k = 0; k < K; ++k)
                 acc = lae2(acc, cur[U * K + k] + to_log2(le[((size_t)(T - 1) * max_u + U - 1) * K + k]));
             llt = acc;
@@ -159,25 +232,46 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         __syncthreads();
         float offB = 0.0f;
         float* bm = srow;                  // Bm(t+1, u), index u+1
+        for (int j = 0; j < kPF; ++j) issue_row(T - 1 - j, true);
         for (int t = T - 1; t >= 0; --t) {
-            const float kt = ((offs[t] - offA_last) + offB) - llt;
+            issue_row(t - kPF, true);
+            cp_async_wait_pf();
+            const float* rle = ring + (size_t)(t % (kPF + 1)) * RS;
+            const float* rls = rle + max_u * K;
+            const float* ral = rls + max_u * K;
+            const float kt = ((soffs[t] - offA_last) + offB) - llt;
             // Bm(t+1,u) = LSE_k(lt(u,k) + beta(t+1,u,k))
             for (int u = tid; u < max_u + 1; u += nt) {
                 float acc = kNeg;
-                if (u < U)
-                    for (int k = 0; k < K; ++k) acc = lae2(acc, tone2[u * K + k] + cur[(u + 1) * K + k]);
+                if (u < U) {
+                    float mx = kNeg;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) mx = fmaxf(mx, tone2[u * K + k] + cur[(u + 1) * K + k]);
+                    if (mx > kNegTest) {
+                        float sum = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sum += ex2((tone2[u * K + k] + cur[(u + 1) * K + k]) - mx);
+                        acc = mx + lg2(sum);
+                    }
+                }
                 bm[u + 1] = acc;
             }
             __syncthreads();
             for (int u = tid; u < max_u; u += nt) {
-                float s_prev = kNeg;  // S(t, u) of this thread's own token (used by token u+1's tone grad)
+                // S(t, u) = LSE_k(alpha(t,u,k) + ls(t,u,k)) of this thread's own token (used by token u+1's
+                // tone gradient): maximum first, the sum of exponentials rides along the main loop
+                float s_max = kNeg, s_sum = 0.0f;
+                if (u < U && !(t == T - 1 || u == U - 1))
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_max = fmaxf(s_max, ral[u * K + k] + to_log2(rls[u * K + k]));
+#pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const size_t o = ((size_t)t * max_u + u) * K + k;
                     float g1 = 0.0f, g2 = 0.0f;
                     if (u < U) {
-                        const float e = to_log2(le[o]);
-                        const float s = (t == T - 1 || u == U - 1) ? kNeg : to_log2(ls[o]);
-                        const float av = scr[(size_t)t * max_u * K + u * K + k];
+                        const float e = to_log2(rle[u * K + k]);
+                        const float s = (t == T - 1 || u == U - 1) ? kNeg : to_log2(rls[u * K + k]);
+                        const float av = ral[u * K + k];
                         const float x = e + cur[(u + 1) * K + k];
                         const float y = s + bm[u + 2];
                         if (!dead) {
@@ -185,13 +279,15 @@ __global__ void tone_fb_kernel(const ToneParams p) {
                             g2 = ex2((av + y) + kt);
                         }
                         nxt[(u + 1) * K + k] = lae2(x, y);
-                        s_prev = lae2(s_prev, av + s);
+                        if (s_max > kNegTest) s_sum += ex2((av + s) - s_max);
                     }
                     ge[o] = g1;
                     gs[o] = g2;
                 }
+                const float s_prev = s_max > kNegTest ? s_max + lg2(s_sum) : kNeg;
                 // entering token u+1 at frame t+1 with tone k: S(t,u) + lt(u+1,k) + beta(t+1,u+1,k)
                 if (u + 1 < U && !dead)
+#pragma unroll
                     for (int k = 0; k < K; ++k)
                         gacc[(u + 1) * K + k] +=
                             ex2(((s_prev + tone2[(u + 1) * K + k]) + cur[(u + 2) * K + k]) + kt);
@@ -264,12 +360,22 @@ void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream) {
     const int K = a.tone_class_size;
     int threads = ((a.max_u + 31) / 32) * 32;
     threads = threads > 1024 ? 1024 : threads;
-    const size_t smem = ((size_t)2 * (a.max_u + 2) * K + (a.max_u + 2) + (size_t)2 * a.max_u * K) * sizeof(float);
+    const size_t smem = ((size_t)2 * (a.max_u + 2) * K + (a.max_u + 2) + (size_t)2 * a.max_u * K +
+                         (size_t)(kPF + 1) * 3 * a.max_u * K + a.max_t) * sizeof(float) + 16;
     SSNT_ASSERT(smem <= 227 * 1024, "tone_latent_forward_backward: max_u * K too large for shared memory");
-    if (smem > 48 * 1024)
-        SSNT_CUDA(cudaFuncSetAttribute(tone_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tone_fb_kernel<<<a.batch_size, threads, smem, stream>>>(p);
-    SSNT_CUDA(cudaGetLastError());
+    auto launch = [&](auto kernel) {
+        if (smem > 48 * 1024)
+            SSNT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<a.batch_size, threads, smem, stream>>>(p);
+        SSNT_CUDA(cudaGetLastError());
+    };
+    switch (K) {
+        case 1: launch(tone_fb_kernel<1>); break;
+        case 2: launch(tone_fb_kernel<2>); break;
+        case 4: launch(tone_fb_kernel<4>); break;
+        case 8: launch(tone_fb_kernel<8>); break;
+        default: launch(tone_fb_kernel<0>); break;
+    }
 }
 
 }  // namespace ssnt
