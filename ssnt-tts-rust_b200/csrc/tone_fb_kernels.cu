@@ -81,7 +81,7 @@ struct ToneParams {
 // shared-memory loads batch); KT == 0: any K.
 template <int KT>
 __global__ void tone_fb_kernel(const ToneParams p) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     __shared__ float red[32];
     __shared__ unsigned s_last;
     const ToneFbArgs& a = p.a;
@@ -119,7 +119,9 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         float* gacc = tone2 + max_u * K;
         // [kPF + 1][3][max_u * K]: le | ls | stored alpha of a row; 16-byte aligned for cp.async
         float* soffs = gacc + max_u * K;  // [max_t] integer row offsets of the stored alpha rows
-        float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(soffs + max_t) + 15) & ~(uintptr_t)15);
+        // (aligned by index arithmetic on the __shared__ array, not by pointer casts: a pointer that went
+        // through uintptr_t is a GENERIC pointer to the compiler and every ring read became an LD.E)
+        float* ring = sm + (((2 * RW + (max_u + 2) + 2 * max_u * K + max_t) + 3) & ~3);
         const int RS = 3 * max_u * K;
         const bool vec16 = (K % 4 == 0) && ((max_u * K) % 4 == 0) && ((reinterpret_cast<uintptr_t>(le) | reinterpret_cast<uintptr_t>(ls) |
                                              reinterpret_cast<uintptr_t>(scr)) % 16 == 0);
