@@ -124,6 +124,15 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
         }
         if (rank == 0 && tid == 0) a.log_likelihood[b] = -INFINITY;
     } else {
+        // Touch what the first stages will read before the cluster barrier: the address translations of a
+        // fresh launch (all recursion CTAs miss the TLB at once, ~3 us) then overlap the barrier.
+        if (rank < 2 && tid < 64) {
+            const int rows = min(2 * kG, T);
+            const int r0 = rank == 0 ? 0 : T - rows;
+            const float* base = (tid < 32 ? a.log_emit : a.log_shift) + (size_t)b * slab + (size_t)r0 * a.max_u;
+            const int nlines = rows * a.max_u / 32;
+            for (int l = tid & 31; l < nlines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 32));
+        }
         for (int i = tid; i < (kSplitHeaderBytes - 128) / 4; i += kSplitThreads) reinterpret_cast<int*>(smem_raw + 128)[i] = 0;
         if (tid == 0) {
             if (rank == 0) p.status[b] = p.force_fallback ? (unsigned)kBfForced : 0u;

@@ -201,9 +201,16 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
         // would otherwise idle until the first stages are prepared, and then run ~80 lines of cold
         // straight-line code through instruction-cache misses.  Its results are thrown away.
         bool warmup = true;
+        int nwarm = 0;
         const ChainState<CPL> cs0 = cs;
         for (int k = 0; k < nst;) {
-            const int ns = nst - k >= 4 ? 4 : (nst - k >= 2 ? 2 : 1);  // stages of this round
+            // stages of this round: four, but the last four go 2, 1, 1 so that the copy-out and the
+            // gradients of the final rows overlap the recursion's last steps (shorter tail)
+            // (starting with small rounds as well was measured slower: the recursion then runs into the
+            // prep warps' first burst and stalls later)
+            const int rem = nst - k;
+            int ns = rem > 4 ? 4 : (rem >= 3 ? 2 : 1);
+            if (warmup) ns = 4;  // the warm-up pass touches the body every full round runs
             const int slot0 = k & (NS - 1);
             const int use = (k >> lgNS) + 1;
             const int* rflag = ready + (slot0 & ~3);  // aligned group of four flags that holds this round's
@@ -257,7 +264,7 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
                 st_warm = tr2 - st_t0;
                 cs = cs0;
                 have_dec = false;
-                warmup = false;
+                warmup = ++nwarm < 1;
                 fl = make_int4(0, 0, 0, 0);
                 continue;
             }
