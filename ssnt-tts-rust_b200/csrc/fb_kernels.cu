@@ -50,8 +50,10 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
     if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, lane, 32);
 }
 
-template <int CPL>
-__global__ void __launch_bounds__(kBfThreads, 1) fb_bf_kernel(const BfParams p) {
+// MINB = 2: throughput variant, two CTAs (of different utterances) per SM — 128 registers per thread and
+// half the shared-memory ring each; their phases interleave, which fills the helpers' idle time.
+template <int CPL, int MINB = 1>
+__global__ void __launch_bounds__(kBfThreads, MINB) fb_bf_kernel(const BfParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
@@ -314,11 +316,11 @@ void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream) {
     SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_log_warp_kernel<CPL>, p));
 }
 
-template <int CPL>
+template <int CPL, int MINB = 1>
 void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
     static size_t configured = 48 * 1024;
     if (smem > configured) {
-        SSNT_CUDA(cudaFuncSetAttribute(fb_bf_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSNT_CUDA(cudaFuncSetAttribute(fb_bf_kernel<CPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -333,7 +335,7 @@ void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_bf_kernel<CPL>, p));
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_bf_kernel<CPL, MINB>, p));
 }
 
 template <int CPL>
@@ -467,6 +469,13 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         int NS = (int)((size_t)(224 * 1024 - kBfHeaderBytes) / stage_bytes);
         NS = NS > 12 ? 12 : NS;
         SSNT_ASSERT(NS >= 4, "forward_backward: ring does not fit shared memory");
+        // Throughput mode (more CTAs than SMs): two CTAs per SM with a 6-stage ring each — for max_u <= 64
+        // only.  Measured at B=1024 U=64: 70 vs 63 G cells/s; at B=512 U=128 the 128-register cap spills
+        // in the recursion and the helpers are the bottleneck anyway: 86 vs 106 G cells/s.
+        bool two_per_sm = (size_t)a.batch_size * 2 > (size_t)sm_count() && a.max_u <= 64 &&
+                          kBfHeaderBytes + 6 * stage_bytes <= 112 * 1024;
+        if (const char* e = std::getenv("SSNT_BF_TWO_PER_SM")) two_per_sm = two_per_sm && std::atoi(e) != 0;  // tuning aid
+        if (two_per_sm) NS = 6;
         p.NS = NS;
         // Few utterances (latency mode): one CTA per SM has to cover the whole HBM latency by
         // itself, so prefetch far ahead; many utterances: neighbours share the L2, stay modest.
@@ -478,7 +487,9 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         if (const char* e = std::getenv("SSNT_BF_DEBUG_SKIP")) p.debug_skip = std::atoi(e);  // profiling aid
         const size_t smem = kBfHeaderBytes + (size_t)NS * stage_bytes;
         const int U = a.max_u;
-        if (U <= 64) launch_bf<2>(p, smem, stream);
+        if (two_per_sm) {
+            launch_bf<2, 2>(p, smem, stream);
+        } else if (U <= 64) launch_bf<2>(p, smem, stream);
         else if (U <= 128) launch_bf<4>(p, smem, stream);
         else launch_bf<8>(p, smem, stream);
         return;

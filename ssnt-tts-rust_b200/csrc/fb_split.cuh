@@ -35,6 +35,15 @@ constexpr int kCopyWarps = 3;   // copy-out warps of a recursion CTA (warps 4, 8
 constexpr int kPrepWarps = 12;  // prep warps of a recursion CTA (sub-partitions 1-3)
 constexpr int kSplitHeaderBytes = 2048;
 constexpr int kPrefetchIters = 2;  // L2 prefetch distance of a prep warp, in its own iterations (x12 stages)
+// Poll intervals of the warps that share an SM with a recursion warp: every probe is a shared-memory load
+// that competes with the recursion's own loads, stores and shuffles.
+#ifndef SSNT_PREP_POLL_NS
+#define SSNT_PREP_POLL_NS 256
+#endif
+#ifndef SSNT_COPY_POLL_NS
+#define SSNT_COPY_POLL_NS 128
+#endif
+constexpr unsigned kPrepPollNs = SSNT_PREP_POLL_NS, kCopyPollNs = SSNT_COPY_POLL_NS;
 constexpr int kRoundRing = 128;  // per-round "rows stored" flags kept by the helpers (value r+1 in slot r % 128)
 
 struct SplitParams {
@@ -324,7 +333,7 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
             constexpr int HR = kG / 2;  // rows per half stage
             if (k >= NS) {  // the slot's previous occupant has been consumed and its state rows copied out
                 const long long t0 = p.stats ? clock64() : 0;
-                wait_flag_ge(slot_free + slot, k / NS, 32);
+                wait_flag_ge(slot_free + slot, k / NS, kPrepPollNs);
                 if (p.stats) st_w1 += clock64() - t0;
             }
             float* dst = slot_ptr(slot);
@@ -405,7 +414,7 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
             for (int k = 2 * r; k < kend; ++k) {
                 const int slot = k % NS;
                 const long long t0 = p.stats ? clock64() : 0;
-                wait_flag_ge(state_done + slot, k / NS + 1, 32);
+                wait_flag_ge(state_done + slot, k / NS + 1, kCopyPollNs);
                 if (p.stats) st_w1 += clock64() - t0;
                 const float* sp = slot_ptr(slot);
                 const int exs = reinterpret_cast<const int*>(sp + stageP + kG * max_u)[lane];
