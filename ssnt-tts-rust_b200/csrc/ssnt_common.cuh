@@ -102,6 +102,11 @@ struct ToneFbArgs {
     size_t workspace_bytes;
 };
 size_t tone_fb_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
+// block-float split-role tone kernel (tone_bf.cu): supported shapes, extra workspace, launch (returns the
+// device [B] status words: non-zero = re-run that utterance in the log domain)
+bool tone_bf_supported(const ToneFbArgs& a);
+size_t tone_bf_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
+unsigned* launch_tone_bf(const ToneFbArgs& a, void* workspace, unsigned* counter, cudaStream_t stream);
 void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream);
 
 }  // namespace ssnt

@@ -1,0 +1,610 @@
+// Tone-latent marginalised lattice, block-floating-point split-role kernel (SURVEY.md §8 a-TL).
+//
+// Same organisation as fb_split.cuh (one cluster of four CTAs per utterance: two recursion CTAs with
+// prep and copy-out warps, two gradient CTAs; flag words in the receiver's shared memory; rows through
+// L2), with a K-vector of tone classes per token:
+//
+//   alpha'(u,k) = alpha(u,k) e(u,k) + tone(u,k) X(u-1),      X(u) = sum_k alpha(u,k) s(u,k)
+//   beta (u,k)  = e(u,k) beta'(u,k) + s(u,k) Y'(u+1),        Y(u) = sum_k tone(u,k) beta(u,k)
+//
+// in the probability domain with one shared power-of-two exponent per lane (its CPL tokens x K tones).
+// A row is max_u*K floats (2 KB at U=128, K=4), so a step carries ~60 instructions of independent
+// work and the one cross-lane value per row (X of the lane's last token / Y of its first) is shuffled
+// at the top of the step and consumed at its end: no skew is needed here.
+//
+// Utterances the block-float arithmetic cannot hold are flagged and re-run by the log-domain kernel
+// (tone_fb_kernels.cu) in a second launch that skips everything else.
+#include "fb_split.cuh"
+
+namespace ssnt {
+using namespace lattice;
+
+namespace {
+
+constexpr int kTThreads = 256;
+constexpr int kTWarps = 8;
+constexpr int kSR = 4;            // rows per stage
+constexpr int kTHeader = 2048;
+constexpr int kTPrepWarps = 5;    // warps 1,2,3,5,6 (sub-partitions 1-3); 4 and 7: copy-out
+constexpr int kTCopyWarps = 2;
+
+struct ToneBfParams {
+    ToneFbArgs a;
+    float* A;          // [B][2][nrows][RW + 32]
+    float* GT;         // [B][2][kTWarps][max_u*K] partial tone gradients
+    unsigned* status;  // [B]
+    int NS, nrows;
+    unsigned* counter;
+};
+
+template <int W>
+__device__ __forceinline__ void ld_row(const float* p, float (&v)[W]) {  // W consecutive floats, 16-byte aligned
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(p + 4 * q);
+        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+}
+template <int W>
+__device__ __forceinline__ void ldcg_row(const float* p, float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 w = __ldcg(reinterpret_cast<const float4*>(p + 4 * q));
+        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+}
+template <int W>
+__device__ __forceinline__ void st_row(float* p, const float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+        *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+template <int W>
+__device__ __forceinline__ void stcs_row(float* p, const float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+        __stcs(reinterpret_cast<float4*>(p + 4 * q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int CPL, int K>
+__device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U, unsigned char* smem_raw) {
+    constexpr int W = CPL * K;              // floats of a row owned by one lane
+    constexpr int RW = 32 * W;              // floats of a row
+    constexpr int RS = RW + 32;             // scratch row stride (lane exponents behind the row)
+    constexpr int slot_floats = 3 * kSR * RW + 32;
+    const ToneFbArgs& a = p.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NS = p.NS, dir = d == 0 ? 1 : -1;
+    const int nst = (T + kSR - 1) / kSR;
+    const size_t slab = (size_t)a.max_t * RW;
+    const float* le = a.log_emit + (size_t)b * slab;
+    const float* ls = a.log_shift + (size_t)b * slab;
+    const float* lt = a.log_tone + (size_t)b * RW;
+    float* Ad = p.A + ((size_t)b * 2 + d) * (size_t)p.nrows * RS;
+    int* ready = reinterpret_cast<int*>(smem_raw + 128);
+    int* state_done = reinterpret_cast<int*>(smem_raw + 256);
+    int* slot_free = reinterpret_cast<int*>(smem_raw + 384);
+    float* ringm = reinterpret_cast<float*>(smem_raw + kTHeader);
+    auto slot_ptr = [&](int slot) { return ringm + (size_t)slot * slot_floats; };
+    const int f0 = lane * W;                // first float of this lane inside a row
+    const bool is_copy = warp == 4 || warp == 7;
+    const int copy_idx = warp == 4 ? 0 : 1;
+    const int prep_idx = warp - 1 - (warp > 4 ? 1 : 0);  // warps 1,2,3,5,6 → 0..4
+
+    if (warp == 0) {
+        // ------------------------------- recursion -------------------------------
+        float tone[W], v[W];
+        {
+            float raw[W];
+            ld_row<W>(lt + f0, raw);
+#pragma unroll
+            for (int i = 0; i < W; ++i) tone[i] = (lane * CPL + i / K < U) ? ex2(raw[i] * kLog2e) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = 0.0f;
+        if (d == 0) {
+            if (lane == 0)
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[k] = tone[k];  // alpha(0,0,k) = tone(0,k)
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i)
+                if (lane * CPL + i / K == U - 1) v[i] = 1.0f;  // virtual terminal row beta(T, U-1, k) = 1
+        }
+        int ex = 0, nb_ex = 0;
+        const bool edge_lane = d == 0 ? lane == 0 : lane == 31;
+        float g = edge_lane ? 0.0f : 1.0f;
+        bool have_dec = false;
+        int ex_dec = 0, nbex_dec = 0;
+        const int lgNS = NS == 8 ? 3 : (NS == 4 ? 2 : 4);
+        int4 fl = make_int4(0, 0, 0, 0);
+        for (int k = 0; k < nst;) {
+            const int rem = nst - k;
+            const int ns = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);  // stages of this round (rounds start at multiples of 4)
+            const int slot0 = k & (NS - 1);
+            const int use = (k >> lgNS) + 1;
+            const int* rflag = ready + (slot0 & ~3);
+            const int fo = slot0 & 3;
+            auto round_ready = [&](const int4& f) {
+                const int q[4] = {f.x, f.y, f.z, f.w};
+                bool ok = true;
+#pragma unroll
+                for (int z = 0; z < 4; ++z)
+                    if (z >= fo && z < fo + ns) ok = ok && q[z] >= use;
+                return ok;
+            };
+            while (!__all_sync(kFull, round_ready(fl)))
+                asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(rflag)) : "memory");
+            {
+                const int* nflag = ready + (((k + ns) & (NS - 1)) & ~3);
+                asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(nflag)) : "memory");
+            }
+            // ---- apply the re-normalisation decided in the previous round ----
+            if (have_dec) {
+                const int shift = ex - ex_dec;
+#pragma unroll
+                for (int i = 0; i < W; ++i) v[i] = scale_pow2(v[i], shift);
+                ex = ex_dec;
+                nb_ex = nbex_dec;
+                g = edge_lane ? 0.0f : pow2i(max(-126, min(126, nb_ex - ex)));
+                have_dec = false;
+            }
+            int own = kNoMass, nbmag = kNoMass;
+            for (int z = 0; z < ns; ++z) {
+                float* sp = slot_ptr((slot0 + z) & (NS - 1));
+                reinterpret_cast<int*>(sp + 3 * kSR * RW)[lane] = ex;
+#pragma unroll
+                for (int q = 0; q < kSR; ++q) {
+                    float E[W], S[W];
+                    ld_row<W>(sp + q * RW + f0, E);
+                    ld_row<W>(sp + (kSR + q) * RW + f0, S);
+                    st_row<W>(sp + (2 * kSR + q) * RW + f0, v);  // the state BEFORE the step is this row
+                    if (d == 0) {
+                        float X[CPL];
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            float x = 0.0f;
+#pragma unroll
+                            for (int kk = 0; kk < K; ++kk) x = fmaf(v[i * K + kk], S[i * K + kk], x);
+                            X[i] = x;
+                        }
+                        const float in = __shfl_up_sync(kFull, X[CPL - 1], 1) * g;
+#pragma unroll
+                        for (int i = CPL - 1; i >= 1; --i)
+#pragma unroll
+                            for (int kk = 0; kk < K; ++kk)
+                                v[i * K + kk] = fmaf(tone[i * K + kk], X[i - 1], v[i * K + kk] * E[i * K + kk]);
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) v[kk] = fmaf(tone[kk], in, v[kk] * E[kk]);
+                    } else {
+                        float Y[CPL];
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            float y = 0.0f;
+#pragma unroll
+                            for (int kk = 0; kk < K; ++kk) y = fmaf(tone[i * K + kk], v[i * K + kk], y);
+                            Y[i] = y;
+                        }
+                        const float in = __shfl_down_sync(kFull, Y[0], 1) * g;
+#pragma unroll
+                        for (int i = 0; i < CPL; ++i) {
+                            const float yn = (i + 1 < CPL) ? Y[i + 1] : in;
+#pragma unroll
+                            for (int kk = 0; kk < K; ++kk)
+                                v[i * K + kk] = fmaf(E[i * K + kk], v[i * K + kk], S[i * K + kk] * yn);
+                        }
+                    }
+                }
+                if (z == ns - 1) {
+                    // decide the next frame from the state two rows... (here: at the round's end; the
+                    // shuffles below overlap the hand-off)
+                    float mx = v[0];
+#pragma unroll
+                    for (int i = 1; i < W; ++i) mx = fmaxf(mx, v[i]);
+                    own = mx > 0.0f ? ex + ilogb_pos(mx) - kTarget : kNoMass;
+                    // magnitude of what the neighbour will receive from the feeding lane
+                    float edge = 0.0f;
+                    if (d == 0) {
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[(CPL - 1) * K + kk]);
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[kk]);
+                    }
+                    const int amag = edge > 0.0f ? ex + ilogb_pos(edge) : kNoMass;
+                    nbmag = d == 0 ? __shfl_up_sync(kFull, amag, 1) : __shfl_down_sync(kFull, amag, 1);
+                    if (edge_lane) nbmag = kNoMass;
+                    int nw = max(own, nbmag - kTarget - kSlack);
+                    if (nw <= kNoMass / 2) nw = ex;
+                    ex_dec = nw;
+                    nbex_dec = d == 0 ? __shfl_up_sync(kFull, nw, 1) : __shfl_down_sync(kFull, nw, 1);
+                    have_dec = true;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                for (int z = 0; z < ns; ++z)
+                    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(state_done + ((slot0 + z) & (NS - 1)))), "r"(use) : "memory");
+            }
+            __syncwarp();
+            k += ns;
+        }
+    } else if (!is_copy) {
+        // ------------------------------- prep -------------------------------
+        bool me[CPL], ms[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            me[i] = lane * CPL + i < U;
+            ms[i] = lane * CPL + i < U - 1;
+        }
+        for (int k = prep_idx; k < nst; k += kTPrepWarps) {
+            const int slot = k & (NS - 1);
+            {
+                const int kf = k + 2 * kTPrepWarps;  // L2 prefetch two iterations ahead, one 128-byte line per lane
+                if (kf < nst) {
+                    const int j0 = kf * kSR, n = min(kSR, T - j0);
+                    const int r0 = dir > 0 ? j0 : T - j0 - n;
+                    const int nlines = n * RW / 32;
+                    for (int l = lane; l < nlines; l += 32) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(le + (size_t)r0 * RW + l * 32));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ls + (size_t)r0 * RW + l * 32));
+                    }
+                }
+            }
+            float RE[kSR][W], RSv[kSR][W];
+#pragma unroll
+            for (int q = 0; q < kSR; ++q) {
+                const int j = k * kSR + q;
+                const int t = dir > 0 ? j : T - 1 - j;
+                if (j < T) {
+                    ldcg_row<W>(le + (size_t)t * RW + f0, RE[q]);
+                    ldcg_row<W>(ls + (size_t)t * RW + f0, RSv[q]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < W; ++i) { RE[q][i] = -INFINITY; RSv[q][i] = -INFINITY; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kSR; ++q) {
+                const int j = k * kSR + q;
+                const int t = dir > 0 ? j : T - 1 - j;
+                const bool not_last = t != T - 1;
+#pragma unroll
+                for (int i = 0; i < W; ++i) {
+                    RE[q][i] = me[i / K] ? ex2(RE[q][i] * kLog2e) : 0.0f;
+                    RSv[q][i] = (ms[i / K] && not_last) ? ex2(RSv[q][i] * kLog2e) : 0.0f;
+                }
+            }
+            if (k >= NS) wait_flag_ge(slot_free + slot, k / NS, 128);
+            float* dst = slot_ptr(slot);
+#pragma unroll
+            for (int q = 0; q < kSR; ++q) {
+                st_row<W>(dst + q * RW + f0, RE[q]);
+                st_row<W>(dst + (kSR + q) * RW + f0, RSv[q]);
+            }
+            __syncwarp();
+            if (lane == 0) flag_publish(ready + slot, k / NS + 1);
+        }
+    } else {
+        // ------------------------------- copy-out -------------------------------
+        const uint32_t h0 = map_to_rank(smem_raw + 1024, 2), h1 = map_to_rank(smem_raw + 1024, 3);
+        const int nround = (nst + 3) / 4;  // publish per four stages (16 rows)
+        for (int r = copy_idx; r < nround; r += kTCopyWarps) {
+            const int kend = min(4 * r + 4, nst);
+            for (int k = 4 * r; k < kend; ++k) {
+                const int slot = k & (NS - 1);
+                wait_flag_ge(state_done + slot, k / NS + 1, 128);
+                const float* sp = slot_ptr(slot);
+                const int exs = reinterpret_cast<const int*>(sp + 3 * kSR * RW)[lane];
+#pragma unroll
+                for (int q = 0; q < kSR; ++q) {
+                    float x[W];
+                    ld_row<W>(sp + (2 * kSR + q) * RW + f0, x);
+                    float* dst = Ad + (size_t)(k * kSR + q) * RS;
+                    st_row<W>(dst + f0, x);
+                    reinterpret_cast<int*>(dst)[RW + lane] = exs;
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(slot_free + slot)), "r"(k / NS + 1) : "memory");
+            }
+            if (lane == 0) {
+                __threadfence();
+                const uint32_t off = 4u * (uint32_t)(d * kRoundRing + (r % kRoundRing));
+                asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(h0 + off), "r"(r + 1) : "memory");
+                asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(h1 + off), "r"(r + 1) : "memory");
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int CPL, int K>
+__device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U, unsigned char* smem_raw) {
+    constexpr int W = CPL * K, RW = 32 * W, RS = RW + 32;
+    constexpr int ROWS = 16;  // rows per published round
+    const ToneFbArgs& a = p.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dir = d == 0 ? 1 : -1;
+    const int m = (T + 1) >> 1;
+    const int n1 = d == 0 ? m - 1 : T - m + 1;
+    const size_t slab = (size_t)a.max_t * RW;
+    const float* le = a.log_emit + (size_t)b * slab;
+    const float* ls = a.log_shift + (size_t)b * slab;
+    const float* lt = a.log_tone + (size_t)b * RW;
+    float* ge = a.grad_emit + (size_t)b * slab;
+    float* gs = a.grad_shift + (size_t)b * slab;
+    const float* A0 = p.A + ((size_t)b * 2 + 0) * (size_t)p.nrows * RS;  // row j = alpha(j)
+    const float* A1 = p.A + ((size_t)b * 2 + 1) * (size_t)p.nrows * RS;  // row j = beta(T - j)
+    float* GT = p.GT + (((size_t)b * 2 + d) * kTWarps + warp) * RW;
+    const int* round_done = reinterpret_cast<const int*>(smem_raw + 1024);
+    int* ll_flag = reinterpret_cast<int*>(smem_raw + 704);
+    float* llinfo = reinterpret_cast<float*>(smem_raw + 720);
+    const int f0 = lane * W;
+
+    auto rows_ready = [&](int dd, int n) {
+        if (n <= 0) return true;
+        const int r = (n - 1) / ROWS;
+        return flag_load(round_done + dd * kRoundRing + (r % kRoundRing)) >= r + 1;
+    };
+    float tone[W], gacc[W];
+    {
+        float raw[W];
+        ld_row<W>(lt + f0, raw);
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            tone[i] = (lane * CPL + i / K < U) ? ex2(raw[i] * kLog2e) : 0.0f;
+            gacc[i] = 0.0f;
+        }
+    }
+    bool me[CPL], ms[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        me[i] = lane * CPL + i < U;
+        ms[i] = lane * CPL + i < U - 1;
+    }
+    float f_inv_sum = 0.0f;
+    int f_M = 0;
+    bool f_dead = false, have_ll = false;
+
+    // one sweep row per work unit; warp w takes the rows n1 + w, n1 + w + 8, ...
+    for (int j = n1 + warp; j < T; j += kTWarps) {
+        const int t = dir > 0 ? j : T - 1 - j;
+        const bool ll_producer = d == 0 && j == n1;
+        while (!(rows_ready(d, j + 1) && rows_ready(1 - d, T - j))) __nanosleep(200);
+        if (!have_ll && !ll_producer) {
+            wait_flag_ge(ll_flag, 1, 200);
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            f_M = __float_as_int(*reinterpret_cast<volatile float*>(llinfo + 0));
+            f_inv_sum = *reinterpret_cast<volatile float*>(llinfo + 1);
+            f_dead = *reinterpret_cast<volatile float*>(llinfo + 2) != 0.0f;
+            have_ll = true;
+        }
+        const float* arow = A0 + (size_t)t * RS;            // alpha(t)
+        const float* brow = A1 + (size_t)(T - 1 - t) * RS;  // beta(t+1)
+        float E[W], S[W], VA[W], VB[W];
+        ldcg_row<W>(le + (size_t)t * RW + f0, E);
+        ldcg_row<W>(ls + (size_t)t * RW + f0, S);
+        ldcg_row<W>(arow + f0, VA);
+        ldcg_row<W>(brow + f0, VB);
+        const int exA = __ldcg(reinterpret_cast<const int*>(arow) + RW + lane);
+        const int exB = __ldcg(reinterpret_cast<const int*>(brow) + RW + lane);
+        const bool not_last = t != T - 1;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            E[i] = me[i / K] ? ex2(E[i] * kLog2e) : 0.0f;
+            S[i] = (ms[i / K] && not_last) ? ex2(S[i] * kLog2e) : 0.0f;
+        }
+        // Y(t+1, u) = sum_k tone(u,k) beta(t+1,u,k) per token; the last token needs lane+1's first
+        float Y[CPL], X[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            float y = 0.0f, x = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                y = fmaf(tone[i * K + kk], VB[i * K + kk], y);
+                x = fmaf(VA[i * K + kk], S[i * K + kk], x);  // X(t,u) = sum_k alpha(t,u,k) s(t,u,k)
+            }
+            Y[i] = y;
+            X[i] = x;
+        }
+        const int exBn = __shfl_down_sync(kFull, exB, 1);
+        float y_edge = scale_pow2(__shfl_down_sync(kFull, Y[0], 1), exBn - exB);
+        if (lane == 31) y_edge = 0.0f;
+        const int exAp = __shfl_up_sync(kFull, exA, 1);
+        float x_edge = scale_pow2(__shfl_up_sync(kFull, X[CPL - 1], 1), exAp - exA);  // X(t, c0-1) in this lane's alpha frame
+        if (lane == 0) x_edge = 0.0f;
+        const int EL = exA + exB;
+        if (ll_producer) {
+            float w = 0.0f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const float yn = (i + 1 < CPL) ? Y[i + 1] : y_edge;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk)
+                    w += VA[i * K + kk] * (E[i * K + kk] * VB[i * K + kk] + S[i * K + kk] * yn);
+            }
+            const bool finite = w == w && w < 3.0e38f;
+            int M = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
+            const float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
+            const float sum = warp_sum(part);
+            const unsigned bad = __ballot_sync(kFull, !finite);
+            unsigned st = 0;
+            if (bad) st |= kBfNonFinite;
+            if (M <= kNoMass / 2 || !(sum > 0.0f)) st |= kBfNoMass;
+            f_M = M;
+            f_inv_sum = st ? 0.0f : 1.0f / sum;
+            f_dead = st != 0;
+            have_ll = true;
+            if (lane == 0) {
+                if (st) atomicOr(p.status + b, st);
+                const double ll2 = (double)lg2(sum) + (double)M;
+                a.log_likelihood[b] = st ? -INFINITY : (float)(ll2 * kLn2);
+                llinfo[0] = __int_as_float(M);
+                llinfo[1] = f_inv_sum;
+                llinfo[2] = f_dead ? 1.0f : 0.0f;
+                __threadfence_block();
+                asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(ll_flag)), "r"(1) : "memory");
+                const uint32_t rl = map_to_rank(llinfo, 3), rf = map_to_rank(ll_flag, 3);
+                asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(rl), "r"(M) : "memory");
+                asm volatile("st.relaxed.cluster.shared::cluster.f32 [%0], %1;" ::"r"(rl + 4u), "f"(f_inv_sum) : "memory");
+                asm volatile("st.relaxed.cluster.shared::cluster.f32 [%0], %1;" ::"r"(rl + 8u), "f"(f_dead ? 1.0f : 0.0f) : "memory");
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(rf), "r"(1) : "memory");
+            }
+        }
+        const int kf = max(-252, min(252, EL - f_M));
+        const int kh = kf >> 1;
+        const float fa = pow2i(max(-126, kh));
+        const float fb = pow2i(max(-126, kf - kh)) * f_inv_sum;
+        float g1[W], g2[W];
+        float occ0 = 0.0f, occT = 0.0f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const float yn = (i + 1 < CPL) ? Y[i + 1] : y_edge;
+            const float xp = (i > 0) ? X[i - 1] : x_edge;  // X(t, u-1): mass that enters token u at frame t+1
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                const int q = i * K + kk;
+                const float va = VA[q] * fa;
+                g1[q] = f_dead ? 0.0f : va * ((E[q] * VB[q]) * fb);
+                g2[q] = f_dead ? 0.0f : va * ((S[q] * yn) * fb);
+                // d LL / d log_tone(u,k): entering token u with tone k at frame t+1
+                if (!f_dead) gacc[q] += (xp * fa) * ((tone[q] * VB[q]) * fb);
+                if (lane == 0 && i == 0) occ0 += g1[q] + g2[q];
+                if (lane * CPL + i == U - 1) occT += g1[q];
+            }
+        }
+        stcs_row<W>(ge + (size_t)t * RW + f0, g1);
+        stcs_row<W>(gs + (size_t)t * RW + f0, g2);
+        if (t == 0 && !f_dead && lane == 0) {
+            // token 0 draws its tone at the start: occupancy of (0, 0, k)
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) gacc[kk] += g1[kk] + g2[kk];
+        }
+        if (!f_dead && (t == T - 1 || t == 0)) {
+            bool bad = false;
+            if (d == 0 && t == T - 1 && (U - 1) / CPL == lane) bad = !(fabsf(occT - 1.0f) < kBfConsistency);
+            if (d == 1 && t == 0 && lane == 0) bad = !(fabsf(occ0 - 1.0f) < kBfConsistency);
+            if (bad) atomicOr(p.status + b, (unsigned)kBfInconsistent);
+        }
+    }
+    st_row<W>(GT + f0, gacc);
+}
+
+template <int CPL, int K>
+__global__ void __launch_bounds__(kTThreads, 1) tone_split_kernel(const ToneBfParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int W = CPL * K, RW = 32 * W;
+    const int tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int b = blockIdx.x >> 2;
+    const ToneFbArgs& a = p.a;
+    int T = a.t_len ? a.t_len[b] : a.max_t;
+    int U = a.u_len ? a.u_len[b] : a.max_u;
+    T = min(max(T, 0), a.max_t);
+    U = min(max(U, 0), a.max_u);
+    const size_t slab = (size_t)a.max_t * RW;
+    if (T <= 0 || U <= 0 || U > T) {
+        if (rank >= 2) {
+            float4* g = reinterpret_cast<float4*>((rank == 2 ? a.grad_emit : a.grad_shift) + (size_t)b * slab);
+            for (size_t i = tid; i < slab / 4; i += kTThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (rank == 0) {
+            for (int i = tid; i < RW; i += kTThreads) a.grad_tone[(size_t)b * RW + i] = 0.0f;
+            if (tid == 0) a.log_likelihood[b] = -INFINITY;
+        }
+    } else {
+        for (int i = tid; i < (kTHeader - 128) / 4; i += kTThreads) reinterpret_cast<int*>(smem_raw + 128)[i] = 0;
+        if (rank == 0 && tid == 0) p.status[b] = 0u;
+        __syncthreads();
+        cluster.sync();
+        if (rank < 2) tone_chain_cta<CPL, K>(p, b, (int)rank, T, U, smem_raw);
+        else tone_grad_cta<CPL, K>(p, b, (int)rank - 2, T, U, smem_raw);
+        if (rank >= 2) {  // padded frames
+            float4* g = reinterpret_cast<float4*>((rank == 2 ? a.grad_emit : a.grad_shift) + (size_t)b * slab + (size_t)T * RW);
+            const size_t n4 = (size_t)(a.max_t - T) * RW / 4;
+            for (size_t i = tid; i < n4; i += kTThreads) __stcs(g + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        __threadfence();
+        cluster.sync();
+        // deterministic reduction of the sixteen per-warp partial tone gradients (rank 0, fixed order)
+        if (rank == 0) {
+            const float* GT = p.GT + (size_t)b * 2 * kTWarps * RW;
+            for (int i = tid; i < RW; i += kTThreads) {
+                float acc = 0.0f;
+                for (int q = 0; q < 2 * kTWarps; ++q) acc += __ldcg(GT + (size_t)q * RW + i);
+                a.grad_tone[(size_t)b * RW + i] = (i / K) < U ? acc : 0.0f;
+            }
+        }
+    }
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kTThreads);
+}
+
+template <int CPL, int K>
+void launch_tone_split(const ToneBfParams& p, size_t smem, cudaStream_t stream) {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(tone_split_kernel<CPL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)p.a.batch_size * 4u);
+    cfg.blockDim = dim3(kTThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, tone_split_kernel<CPL, K>, p));
+}
+
+}  // namespace
+
+// Shapes the block-float tone kernel takes: K = 4, max_u in {32, 64, 128}, 16-byte aligned tensors.
+bool tone_bf_supported(const ToneFbArgs& a) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    return a.tone_class_size == 4 && (a.max_u == 32 || a.max_u == 64 || a.max_u == 128) && al(a.log_emit) &&
+           al(a.log_shift) && al(a.log_tone) && al(a.grad_emit) && al(a.grad_shift) && al(a.grad_tone);
+}
+size_t tone_bf_workspace_bytes(int B, int max_t, int max_u, int K) {
+    if (K != 4 || !(max_u == 32 || max_u == 64 || max_u == 128)) return 0;
+    const size_t RW = (size_t)max_u * K, RS = RW + 32;
+    const size_t nrows = (((size_t)max_t + kSR - 1) / kSR) * kSR;
+    return ((size_t)B * 2 * nrows * RS + (size_t)B * 2 * kTWarps * RW) * sizeof(float) +
+           (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255) + 512;
+}
+// Runs the block-float kernel; returns the device pointer of the [B] status words (non-zero = utterance
+// must be re-run in the log domain).
+unsigned* launch_tone_bf(const ToneFbArgs& a, void* ws, unsigned* counter, cudaStream_t stream) {
+    ToneBfParams p;
+    p.a = a;
+    const int K = 4;
+    const size_t RW = (size_t)a.max_u * K, RS = RW + 32;
+    p.nrows = ((a.max_t + kSR - 1) / kSR) * kSR;
+    p.A = (float*)ws;
+    p.GT = p.A + (size_t)a.batch_size * 2 * p.nrows * RS;
+    p.status = (unsigned*)(p.GT + (size_t)a.batch_size * 2 * kTWarps * RW);
+    p.counter = counter;
+    const size_t slot_bytes = ((size_t)3 * kSR * RW + 32) * sizeof(float);
+    int NS = (int)((size_t)(224 * 1024 - kTHeader) / slot_bytes);
+    NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);
+    p.NS = NS;
+    const size_t smem = kTHeader + (size_t)NS * slot_bytes;
+    if (a.max_u == 32) launch_tone_split<1, 4>(p, smem, stream);
+    else if (a.max_u == 64) launch_tone_split<2, 4>(p, smem, stream);
+    else launch_tone_split<4, 4>(p, smem, stream);
+    return p.status;
+}
+
+}  // namespace ssnt

@@ -75,6 +75,9 @@ struct ToneParams {
     float* scratch;  // [B][T][U][K] alpha~
     float* offs;     // [B][T]
     unsigned* counter;
+    unsigned* fallbacks;   // cumulative count of re-run utterances (ssnt_tts_fb_fallback_count)
+    const unsigned* only;  // optional [B]: run only the utterances whose word is non-zero (re-run of the
+                           // ones the block-float kernel flagged); the others keep their results
 };
 
 // KT > 0: tone_class_size known at compile time (the loops over the tones unroll and their
@@ -105,11 +108,15 @@ __global__ void tone_fb_kernel(const ToneParams p) {
     const bool infeasible = T <= 0 || U <= 0 || U > T;
     float llt = 0.0f, offA_last = 0.0f;
     bool dead = true;
-    if (infeasible) {
+    if (p.only && p.only[b] == 0) {
+        // nothing to redo for this utterance; it still takes part in the loss reduction below
+    } else if (infeasible) {
+        if (p.only && tid == 0) atomicAdd(p.fallbacks, 1u);
         for (size_t i = tid; i < slab; i += nt) { ge[i] = 0.0f; gs[i] = 0.0f; }
         for (int i = tid; i < max_u * K; i += nt) gt[i] = 0.0f;
         if (tid == 0) a.log_likelihood[b] = -INFINITY;
     } else {
+        if (p.only && tid == 0) atomicAdd(p.fallbacks, 1u);
         // shared layout: cur[(U+2)*K], nxt[(U+2)*K], srow[U+2], tone2[U*K], gacc[U*K]
         const int RW = (max_u + 2) * K;
         float* cur = sm;
@@ -337,7 +344,8 @@ __global__ void tone_fb_kernel(const ToneParams p) {
 size_t tone_fb_workspace_bytes(int B, int max_t, int max_u, int K) {
     if (B <= 0 || max_t <= 0 || max_u <= 0 || K <= 0) return 256;
     size_t n = ((size_t)B * max_t * max_u * K + (size_t)B * max_t) * sizeof(float);
-    return (n + 255) & ~(size_t)255;
+    n = (n + 255) & ~(size_t)255;
+    return n + tone_bf_workspace_bytes(B, max_t, max_u, K);
 }
 
 void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream) {
@@ -354,12 +362,20 @@ void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream) {
     } else {
         ws = device_scratch(1, need);
     }
+    const int K = a.tone_class_size;
+    const size_t log_bytes = (((size_t)a.batch_size * a.max_t * a.max_u * K + (size_t)a.batch_size * a.max_t) * sizeof(float) + 255) & ~(size_t)255;
+    // Block-float split-role kernel first (tone_bf.cu); the log-domain kernel then redoes only what it flagged.
+    const unsigned* only = nullptr;
+    bool use_bf = tone_bf_supported(a) && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0;
+    if (const char* e = std::getenv("SSNT_TONE_BF")) use_bf = use_bf && std::atoi(e) != 0;  // tuning / test aid
+    if (use_bf) only = launch_tone_bf(a, (char*)ws + log_bytes, next_done_counter(), stream);
     ToneParams p;
     p.a = a;
     p.scratch = (float*)ws;
     p.offs = (float*)ws + (size_t)a.batch_size * a.max_t * a.max_u * a.tone_class_size;
     p.counter = next_done_counter();
-    const int K = a.tone_class_size;
+    p.only = only;
+    p.fallbacks = device_fallback_counter();
     int threads = ((a.max_u + 31) / 32) * 32;
     threads = threads > 1024 ? 1024 : threads;
     const size_t smem = ((size_t)2 * (a.max_u + 2) * K + (a.max_u + 2) + (size_t)2 * a.max_u * K +

@@ -312,3 +312,65 @@ def test_auto_dispatch_small_and_large_batches(product):
         assert product.fb_kernel_used() == want_kind
         rows = (ge + gs).sum(dim=2)
         assert torch.allclose(rows, torch.ones_like(rows), atol=2e-4)
+
+
+# ---- tone-latent lattice: block-float split-role kernel (K = 4, max_u in {32, 64, 128}) ------------------------
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,T,U", [(2, 40, 32), (3, 100, 64), (2, 300, 128), (1, 801, 128), (35, 64, 32), (2, 5, 32)])
+@pytest.mark.parametrize("bf", ["1", "0"])
+def test_tone_latent_block_float_and_log_kernels(product, oracle_mod, monkeypatch, B, T, U, bf):
+    """Shapes the block-float tone kernel takes (bf=1) against the fp64 oracle, ragged lengths; bf=0 runs the
+    log-domain kernel on the same inputs (SSNT_TONE_BF=0), so both paths are pinned to the same vectors."""
+    monkeypatch.setenv("SSNT_TONE_BF", bf)
+    K = 4
+    le, ls, lt = make_inputs(B, T, U, seed=T + U, K=K)
+    rng = np.random.default_rng(T * 3 + U)
+    t_len = rng.integers(max(1, T // 2), T + 1, B).astype(np.int32)
+    u_len = np.array([rng.integers(1, min(U, tb) + 1) for tb in t_len], np.int32)
+    t_len[0] = T
+    u_len[0] = min(U, T)
+    want = oracle_mod.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
+    ll, loss, ge, gs, gt = (_np(g) for g in got)
+    finite = np.isfinite(want[0])
+    assert np.array_equal(np.isfinite(ll), finite)
+    assert np.all(np.abs(ll[finite] - want[0][finite]) <= LL_RTOL * np.abs(want[0][finite]) + 1e-6)
+    for b in range(B):
+        scale = max(float(np.abs(want[2][b]).max()), 1e-30)
+        assert np.abs(ge[b] - want[2][b]).max() <= GRAD_RTOL * scale
+        assert np.abs(gs[b] - want[3][b]).max() <= GRAD_RTOL * scale
+        # tone gradients are sums of occupancies over frames: scale by their own maximum
+        assert np.abs(gt[b] - want[4][b]).max() <= GRAD_RTOL * max(1.0, float(np.abs(want[4][b]).max()))
+        assert not ge[b, t_len[b]:].any() and not gs[b, t_len[b]:].any()
+        assert not ge[b, :, u_len[b]:].any() and not gt[b, u_len[b]:].any()
+
+
+@pytest.mark.timeout(180)
+def test_tone_latent_config3_properties(product):
+    """BASELINE configs[2] at full size (B=32 U=128 T=800 K=4): per-frame occupancies sum to 1, every
+    token draws exactly one tone (sum_k grad_tone[u,k] = 1), expected shifts = U-1."""
+    import torch
+    B, T, U, K = 32, 800, 128, 4
+    g = torch.Generator(device="cuda").manual_seed(7)
+    z = torch.randn(B, T, U, K, device="cuda", generator=g)
+    le, ls = torch.nn.functional.logsigmoid(z), torch.nn.functional.logsigmoid(-z)
+    lt = torch.log_softmax(torch.randn(B, U, K, device="cuda", generator=g), dim=-1)
+    ll, loss, ge, gs, gt = product.tone_latent_forward_backward(le, ls, lt)
+    torch.cuda.synchronize()
+    rows = (ge + gs).sum(dim=(2, 3))
+    assert torch.allclose(rows, torch.ones_like(rows), atol=3e-4)
+    assert torch.allclose(gt.sum(dim=2), torch.ones(B, U, device="cuda"), atol=3e-4)
+    assert torch.allclose(gs.sum(dim=(1, 2, 3)), torch.full((B,), float(U - 1), device="cuda"), rtol=1e-4)
+    assert torch.allclose(loss[0], -ll.double().sum().float(), rtol=1e-6)
+
+
+def test_tone_latent_block_float_does_not_fall_back_on_typical_inputs(product):
+    import torch
+    B, T, U, K = 8, 400, 128, 4
+    z = torch.randn(B, T, U, K, device="cuda")
+    le, ls = torch.nn.functional.logsigmoid(z), torch.nn.functional.logsigmoid(-z)
+    lt = torch.log_softmax(torch.randn(B, U, K, device="cuda"), dim=-1)
+    before = product.fb_fallback_count()
+    product.tone_latent_forward_backward(le, ls, lt)
+    torch.cuda.synchronize()
+    assert product.fb_fallback_count() == before
