@@ -66,6 +66,34 @@ __device__ __forceinline__ void stcs_row(float* p, const float (&v)[W]) {
         __stcs(reinterpret_cast<float4*>(p + 4 * q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
 }
 
+// Lane-interleaved row layout for everything this kernel owns (shared-memory ring, scratch rows A): the
+// q-th float4 of lane l sits at float offset (q*32 + l)*4, so one 128-bit access of a warp covers 512
+// contiguous bytes.  In the natural layout (a lane's W floats contiguous, lanes 4*W bytes apart) every
+// 128-bit shared-memory access is a 4-way bank conflict at W = 16 (measured: the recursion CTA was
+// shared-memory-bandwidth bound at ~1100 cycles per row).
+template <int W>
+__device__ __forceinline__ void ldp_row(const float* row, int lane, float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(row + (q * 32 + lane) * 4);
+        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+}
+template <int W>
+__device__ __forceinline__ void ldcgp_row(const float* row, int lane, float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+        const float4 w = __ldcg(reinterpret_cast<const float4*>(row + (q * 32 + lane) * 4));
+        v[4 * q] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+    }
+}
+template <int W>
+__device__ __forceinline__ void stp_row(float* row, int lane, const float (&v)[W]) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+        *reinterpret_cast<float4*>(row + (q * 32 + lane) * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 template <int CPL, int K>
 __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U, unsigned char* smem_raw) {
@@ -121,7 +149,8 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
         int4 fl = make_int4(0, 0, 0, 0);
         for (int k = 0; k < nst;) {
             const int rem = nst - k;
-            const int ns = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);  // stages of this round (rounds start at multiples of 4)
+            const int ns = rem >= 2 ? 2 : 1;  // stages of this round: 8 rows (the ring holds 8 stages; short rounds
+                                              // recycle slots early enough for the prep warps to stay ahead)
             const int slot0 = k & (NS - 1);
             const int use = (k >> lgNS) + 1;
             const int* rflag = ready + (slot0 & ~3);
@@ -142,6 +171,13 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(nflag)) : "memory");
             }
+            // the state region of these slots still holds the rows of NS stages ago until the copy-out
+            // warps have moved them (almost always long done: probe once, then poll)
+            if (use > 1) {
+                for (int z = 0; z < ns; ++z)
+                    while (!__all_sync(kFull, flag_load(slot_free + ((slot0 + z) & (NS - 1))) >= use - 1)) {
+                    }
+            }
             // ---- apply the re-normalisation decided in the previous round ----
             if (have_dec) {
                 const int shift = ex - ex_dec;
@@ -159,9 +195,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
 #pragma unroll
                 for (int q = 0; q < kSR; ++q) {
                     float E[W], S[W];
-                    ld_row<W>(sp + q * RW + f0, E);
-                    ld_row<W>(sp + (kSR + q) * RW + f0, S);
-                    st_row<W>(sp + (2 * kSR + q) * RW + f0, v);  // the state BEFORE the step is this row
+                    ldp_row<W>(sp + q * RW, lane, E);
+                    ldp_row<W>(sp + (kSR + q) * RW, lane, S);
+                    stp_row<W>(sp + (2 * kSR + q) * RW, lane, v);  // the state BEFORE the step is this row
                     if (d == 0) {
                         float X[CPL];
 #pragma unroll
@@ -279,12 +315,13 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                     RSv[q][i] = (ms[i / K] && not_last) ? ex2(RSv[q][i] * kLog2e) : 0.0f;
                 }
             }
-            if (k >= NS) wait_flag_ge(slot_free + slot, k / NS, 128);
+            // the slot's e/s region is free once the recursion has consumed its previous occupant
+            if (k >= NS) wait_flag_ge(state_done + slot, k / NS, 128);
             float* dst = slot_ptr(slot);
 #pragma unroll
             for (int q = 0; q < kSR; ++q) {
-                st_row<W>(dst + q * RW + f0, RE[q]);
-                st_row<W>(dst + (kSR + q) * RW + f0, RSv[q]);
+                stp_row<W>(dst + q * RW, lane, RE[q]);
+                stp_row<W>(dst + (kSR + q) * RW, lane, RSv[q]);
             }
             __syncwarp();
             if (lane == 0) flag_publish(ready + slot, k / NS + 1);
@@ -303,9 +340,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
 #pragma unroll
                 for (int q = 0; q < kSR; ++q) {
                     float x[W];
-                    ld_row<W>(sp + (2 * kSR + q) * RW + f0, x);
+                    ldp_row<W>(sp + (2 * kSR + q) * RW, lane, x);
                     float* dst = Ad + (size_t)(k * kSR + q) * RS;
-                    st_row<W>(dst + f0, x);
+                    stp_row<W>(dst, lane, x);  // the scratch rows keep the interleaved layout
                     reinterpret_cast<int*>(dst)[RW + lane] = exs;
                 }
                 __syncwarp();
@@ -388,8 +425,8 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
         float E[W], S[W], VA[W], VB[W];
         ldcg_row<W>(le + (size_t)t * RW + f0, E);
         ldcg_row<W>(ls + (size_t)t * RW + f0, S);
-        ldcg_row<W>(arow + f0, VA);
-        ldcg_row<W>(brow + f0, VB);
+        ldcgp_row<W>(arow, lane, VA);
+        ldcgp_row<W>(brow, lane, VB);
         const int exA = __ldcg(reinterpret_cast<const int*>(arow) + RW + lane);
         const int exB = __ldcg(reinterpret_cast<const int*>(brow) + RW + lane);
         const bool not_last = t != T - 1;
