@@ -388,6 +388,7 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
 
 int fb_last_kernel_kind() { return tls_last_kind; }
 void fb_set_stats_buffer(long long* dev) { tls_stats = dev; }
+long long* fb_get_stats_buffer() { return tls_stats; }
 void fb_force_kernel_kind(int kind) { tls_force_kind = kind; }
 
 void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {

@@ -84,7 +84,8 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream);
 // lattice kernel, 0 = generic block kernel); for tests and the bench's launch accounting.
 int fb_last_kernel_kind();
 void fb_force_kernel_kind(int kind);  // -1 auto, 0 generic, 1 log-warp, 2 block-float, 3 = 2 + forced re-run
-void fb_set_stats_buffer(long long* dev);  // profiling aid for the block-float kernel (null = off)
+void fb_set_stats_buffer(long long* dev);
+long long* fb_get_stats_buffer();  // profiling aid for the block-float kernel (null = off)
 
 struct ToneFbArgs {
     const float* log_emit;   // [B,T,U,K]

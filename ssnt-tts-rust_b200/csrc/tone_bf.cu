@@ -35,6 +35,7 @@ struct ToneBfParams {
     unsigned* status;  // [B]
     int NS, nrows;
     unsigned* counter;
+    long long* stats;  // profiling aid: [4B CTAs][8 warps][8] cycle counters, or null
 };
 
 template <int W>
@@ -147,6 +148,8 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
         int ex_dec = 0, nbex_dec = 0;
         const int lgNS = NS == 8 ? 3 : (NS == 4 ? 2 : 4);
         int4 fl = make_int4(0, 0, 0, 0);
+        const long long st0 = p.stats ? clock64() : 0;
+        long long st_w = 0, st_f = 0;
         for (int k = 0; k < nst;) {
             const int rem = nst - k;
             const int ns = rem >= 2 ? 2 : 1;  // stages of this round: 8 rows (the ring holds 8 stages; short rounds
@@ -163,9 +166,12 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                     if (z >= fo && z < fo + ns) ok = ok && q[z] >= use;
                 return ok;
             };
+            const long long tw0 = p.stats ? clock64() : 0;
             while (!__all_sync(kFull, round_ready(fl)))
                 asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(rflag)) : "memory");
+            const long long tw1 = p.stats ? clock64() : 0;
+            st_w += tw1 - tw0;
             {
                 const int* nflag = ready + (((k + ns) & (NS - 1)) & ~3);
                 asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
@@ -178,6 +184,7 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                     while (!__all_sync(kFull, flag_load(slot_free + ((slot0 + z) & (NS - 1))) >= use - 1)) {
                     }
             }
+            if (p.stats) st_f += clock64() - tw1;
             // ---- apply the re-normalisation decided in the previous round ----
             if (have_dec) {
                 const int shift = ex - ex_dec;
@@ -189,22 +196,37 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 have_dec = false;
             }
             int own = kNoMass, nbmag = kNoMass;
-            for (int z = 0; z < ns; ++z) {
-                float* sp = slot_ptr((slot0 + z) & (NS - 1));
-                reinterpret_cast<int*>(sp + 3 * kSR * RW)[lane] = ex;
-#pragma unroll
-                for (int q = 0; q < kSR; ++q) {
-                    float E[W], S[W];
-                    ldp_row<W>(sp + q * RW, lane, E);
-                    ldp_row<W>(sp + (kSR + q) * RW, lane, S);
-                    stp_row<W>(sp + (2 * kSR + q) * RW, lane, v);  // the state BEFORE the step is this row
+            for (int z = 0; z < ns; ++z)
+                reinterpret_cast<int*>(slot_ptr((slot0 + z) & (NS - 1)) + 3 * kSR * RW)[lane] = ex;
+            // rows of the round, the next row's probabilities requested before the current row is computed
+            // (the compiler cannot hoist those loads itself: they might alias the state rows stored in between)
+            const int nrow = ns * kSR;
+            float E[2][W], S[2][W];
+            {
+                const float* sp0 = slot_ptr(slot0);
+                ldp_row<W>(sp0, lane, E[0]);
+                ldp_row<W>(sp0 + kSR * RW, lane, S[0]);
+            }
+#pragma unroll 2
+            for (int r = 0; r < nrow; ++r) {
+                float* sp = slot_ptr((slot0 + (r >> 2)) & (NS - 1));
+                const int q = r & (kSR - 1);
+                const int cb = r & 1;
+                if (r + 1 < nrow) {
+                    const float* spn = slot_ptr((slot0 + ((r + 1) >> 2)) & (NS - 1));
+                    const int qn = (r + 1) & (kSR - 1);
+                    if (cb == 0) { ldp_row<W>(spn + qn * RW, lane, E[1]); ldp_row<W>(spn + (kSR + qn) * RW, lane, S[1]); }
+                    else { ldp_row<W>(spn + qn * RW, lane, E[0]); ldp_row<W>(spn + (kSR + qn) * RW, lane, S[0]); }
+                }
+                stp_row<W>(sp + (2 * kSR + q) * RW, lane, v);  // the state BEFORE the step is this row
+                auto step = [&](const float (&Ec)[W], const float (&Sc)[W]) {
                     if (d == 0) {
                         float X[CPL];
 #pragma unroll
                         for (int i = 0; i < CPL; ++i) {
                             float x = 0.0f;
 #pragma unroll
-                            for (int kk = 0; kk < K; ++kk) x = fmaf(v[i * K + kk], S[i * K + kk], x);
+                            for (int kk = 0; kk < K; ++kk) x = fmaf(v[i * K + kk], Sc[i * K + kk], x);
                             X[i] = x;
                         }
                         const float in = __shfl_up_sync(kFull, X[CPL - 1], 1) * g;
@@ -212,9 +234,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                         for (int i = CPL - 1; i >= 1; --i)
 #pragma unroll
                             for (int kk = 0; kk < K; ++kk)
-                                v[i * K + kk] = fmaf(tone[i * K + kk], X[i - 1], v[i * K + kk] * E[i * K + kk]);
+                                v[i * K + kk] = fmaf(tone[i * K + kk], X[i - 1], v[i * K + kk] * Ec[i * K + kk]);
 #pragma unroll
-                        for (int kk = 0; kk < K; ++kk) v[kk] = fmaf(tone[kk], in, v[kk] * E[kk]);
+                        for (int kk = 0; kk < K; ++kk) v[kk] = fmaf(tone[kk], in, v[kk] * Ec[kk]);
                     } else {
                         float Y[CPL];
 #pragma unroll
@@ -230,35 +252,35 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                             const float yn = (i + 1 < CPL) ? Y[i + 1] : in;
 #pragma unroll
                             for (int kk = 0; kk < K; ++kk)
-                                v[i * K + kk] = fmaf(E[i * K + kk], v[i * K + kk], S[i * K + kk] * yn);
+                                v[i * K + kk] = fmaf(Ec[i * K + kk], v[i * K + kk], Sc[i * K + kk] * yn);
                         }
                     }
+                };
+                if (cb == 0) step(E[0], S[0]);
+                else step(E[1], S[1]);
+            }
+            {
+                // decide the next frame from the state at the round's end (the shuffles overlap the hand-off)
+                float mx = v[0];
+#pragma unroll
+                for (int i = 1; i < W; ++i) mx = fmaxf(mx, v[i]);
+                own = mx > 0.0f ? ex + ilogb_pos(mx) - kTarget : kNoMass;
+                float edge = 0.0f;  // magnitude of what the neighbour lane will receive from this one
+                if (d == 0) {
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[(CPL - 1) * K + kk]);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[kk]);
                 }
-                if (z == ns - 1) {
-                    // decide the next frame from the state two rows... (here: at the round's end; the
-                    // shuffles below overlap the hand-off)
-                    float mx = v[0];
-#pragma unroll
-                    for (int i = 1; i < W; ++i) mx = fmaxf(mx, v[i]);
-                    own = mx > 0.0f ? ex + ilogb_pos(mx) - kTarget : kNoMass;
-                    // magnitude of what the neighbour will receive from the feeding lane
-                    float edge = 0.0f;
-                    if (d == 0) {
-#pragma unroll
-                        for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[(CPL - 1) * K + kk]);
-                    } else {
-#pragma unroll
-                        for (int kk = 0; kk < K; ++kk) edge = fmaxf(edge, v[kk]);
-                    }
-                    const int amag = edge > 0.0f ? ex + ilogb_pos(edge) : kNoMass;
-                    nbmag = d == 0 ? __shfl_up_sync(kFull, amag, 1) : __shfl_down_sync(kFull, amag, 1);
-                    if (edge_lane) nbmag = kNoMass;
-                    int nw = max(own, nbmag - kTarget - kSlack);
-                    if (nw <= kNoMass / 2) nw = ex;
-                    ex_dec = nw;
-                    nbex_dec = d == 0 ? __shfl_up_sync(kFull, nw, 1) : __shfl_down_sync(kFull, nw, 1);
-                    have_dec = true;
-                }
+                const int amag = edge > 0.0f ? ex + ilogb_pos(edge) : kNoMass;
+                nbmag = d == 0 ? __shfl_up_sync(kFull, amag, 1) : __shfl_down_sync(kFull, amag, 1);
+                if (edge_lane) nbmag = kNoMass;
+                int nw = max(own, nbmag - kTarget - kSlack);
+                if (nw <= kNoMass / 2) nw = ex;
+                ex_dec = nw;
+                nbex_dec = d == 0 ? __shfl_up_sync(kFull, nw, 1) : __shfl_down_sync(kFull, nw, 1);
+                have_dec = true;
             }
             __syncwarp();
             if (lane == 0) {
@@ -269,6 +291,10 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
             __syncwarp();
             k += ns;
         }
+        if (p.stats && lane == 0) {
+            long long* o = p.stats + ((size_t)blockIdx.x * 8 + warp) * 8;
+            o[0] = clock64() - st0; o[1] = st_w; o[2] = st_f;
+        }
     } else if (!is_copy) {
         // ------------------------------- prep -------------------------------
         bool me[CPL], ms[CPL];
@@ -277,6 +303,8 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
             me[i] = lane * CPL + i < U;
             ms[i] = lane * CPL + i < U - 1;
         }
+        const long long st0 = p.stats ? clock64() : 0;
+        long long st_w = 0;
         for (int k = prep_idx; k < nst; k += kTPrepWarps) {
             const int slot = k & (NS - 1);
             {
@@ -316,7 +344,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 }
             }
             // the slot's e/s region is free once the recursion has consumed its previous occupant
-            if (k >= NS) wait_flag_ge(state_done + slot, k / NS, 128);
+            { const long long t0 = p.stats ? clock64() : 0;
+              if (k >= NS) wait_flag_ge(state_done + slot, k / NS, 128);
+              if (p.stats) st_w += clock64() - t0; }
             float* dst = slot_ptr(slot);
 #pragma unroll
             for (int q = 0; q < kSR; ++q) {
@@ -325,6 +355,10 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
             }
             __syncwarp();
             if (lane == 0) flag_publish(ready + slot, k / NS + 1);
+        }
+        if (p.stats && lane == 0) {
+            long long* o = p.stats + ((size_t)blockIdx.x * 8 + warp) * 8;
+            o[0] = clock64() - st0; o[1] = st_w;
         }
     } else {
         // ------------------------------- copy-out -------------------------------
@@ -407,11 +441,26 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
     int f_M = 0;
     bool f_dead = false, have_ll = false;
 
-    // one sweep row per work unit; warp w takes the rows n1 + w, n1 + w + 8, ...
-    for (int j = n1 + warp; j < T; j += kTWarps) {
+    // one sweep row per work unit; warp w takes the rows n1 + w, n1 + w + 8, ...  The next row's loads are
+    // issued before the current row is computed (two register sets): a row's inputs come from L2/HBM
+    // (~2-3 k cycles) and eight warps with one row in flight each cannot hide that.
+    const long long st0 = p.stats ? clock64() : 0;
+    long long st_w = 0, st_start = 0;
+    auto ready = [&](int jj) { return rows_ready(d, jj + 1) && rows_ready(1 - d, T - jj); };
+    auto load = [&](int jj, float (&E)[W], float (&S)[W], float (&VA)[W], float (&VB)[W], int& exA, int& exB) {
+        const int t = dir > 0 ? jj : T - 1 - jj;
+        const float* arow = A0 + (size_t)t * RS;            // alpha(t)
+        const float* brow = A1 + (size_t)(T - 1 - t) * RS;  // beta(t+1)
+        ldcg_row<W>(le + (size_t)t * RW + f0, E);
+        ldcg_row<W>(ls + (size_t)t * RW + f0, S);
+        ldcgp_row<W>(arow, lane, VA);
+        ldcgp_row<W>(brow, lane, VB);
+        exA = __ldcg(reinterpret_cast<const int*>(arow) + RW + lane);
+        exB = __ldcg(reinterpret_cast<const int*>(brow) + RW + lane);
+    };
+    auto compute = [&](int j, float (&E)[W], float (&S)[W], float (&VA)[W], float (&VB)[W], const int exA, const int exB) {
         const int t = dir > 0 ? j : T - 1 - j;
         const bool ll_producer = d == 0 && j == n1;
-        while (!(rows_ready(d, j + 1) && rows_ready(1 - d, T - j))) __nanosleep(200);
         if (!have_ll && !ll_producer) {
             wait_flag_ge(ll_flag, 1, 200);
             asm volatile("fence.acq_rel.cluster;" ::: "memory");
@@ -420,15 +469,6 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
             f_dead = *reinterpret_cast<volatile float*>(llinfo + 2) != 0.0f;
             have_ll = true;
         }
-        const float* arow = A0 + (size_t)t * RS;            // alpha(t)
-        const float* brow = A1 + (size_t)(T - 1 - t) * RS;  // beta(t+1)
-        float E[W], S[W], VA[W], VB[W];
-        ldcg_row<W>(le + (size_t)t * RW + f0, E);
-        ldcg_row<W>(ls + (size_t)t * RW + f0, S);
-        ldcgp_row<W>(arow, lane, VA);
-        ldcgp_row<W>(brow, lane, VB);
-        const int exA = __ldcg(reinterpret_cast<const int*>(arow) + RW + lane);
-        const int exB = __ldcg(reinterpret_cast<const int*>(brow) + RW + lane);
         const bool not_last = t != T - 1;
 #pragma unroll
         for (int i = 0; i < W; ++i) {
@@ -530,8 +570,55 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
             if (d == 1 && t == 0 && lane == 0) bad = !(fabsf(occ0 - 1.0f) < kBfConsistency);
             if (bad) atomicOr(p.status + b, (unsigned)kBfInconsistent);
         }
+    };
+    // L2 prefetch of a future row's four inputs (2 KB each): 17 lines per array, 64 lines over 32 lanes x 2.
+    // The working set (inputs 105 MB + scratch rows 111 MB at config 3) does not live in L2, so without this
+    // every row pays an HBM round trip with only two rows in flight per warp.
+    auto prefetch_row = [&](int jj) {
+        if (jj >= T) return;
+        const int t = dir > 0 ? jj : T - 1 - jj;
+        const float* src[4] = {le + (size_t)t * RW, ls + (size_t)t * RW, A0 + (size_t)t * RS, A1 + (size_t)(T - 1 - t) * RS};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int nl = (r < 2 ? RW : RS) / 32 + (r < 2 ? 0 : 1);
+            if (lane < nl) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[r] + lane * 32));
+        }
+    };
+    auto wait_ready = [&](int jj) {
+        const long long tw0 = p.stats ? clock64() : 0;
+        while (!ready(jj)) __nanosleep(200);
+        if (p.stats) { const long long t1 = clock64(); st_w += t1 - tw0; if (!st_start) st_start = t1 - st0; }
+    };
+    {
+        float EA[W], SA[W], VAA[W], VBA[W], EB[W], SB[W], VAB[W], VBB[W];
+        int xAA = 0, xBA = 0, xAB = 0, xBB = 0;
+        bool hasA = false, hasB = false;
+        int j = n1 + warp;
+        constexpr int kAhead = 4;  // prefetch distance in this warp's own rows (x8 sweep rows)
+        for (int q = 1; q <= kAhead; ++q) prefetch_row(j + q * kTWarps);
+        while (j < T) {
+            prefetch_row(j + (kAhead + 1) * kTWarps);
+            prefetch_row(j + (kAhead + 2) * kTWarps);
+            if (!hasA) { wait_ready(j); load(j, EA, SA, VAA, VBA, xAA, xBA); }
+            hasA = false;
+            const int j2 = j + kTWarps;
+            if (j2 < T && ready(j2)) { load(j2, EB, SB, VAB, VBB, xAB, xBB); hasB = true; }
+            compute(j, EA, SA, VAA, VBA, xAA, xBA);
+            j = j2;
+            if (j >= T) break;
+            if (!hasB) { wait_ready(j); load(j, EB, SB, VAB, VBB, xAB, xBB); }
+            hasB = false;
+            const int j3 = j + kTWarps;
+            if (j3 < T && ready(j3)) { load(j3, EA, SA, VAA, VBA, xAA, xBA); hasA = true; }
+            compute(j, EB, SB, VAB, VBB, xAB, xBB);
+            j = j3;
+        }
     }
     st_row<W>(GT + f0, gacc);
+    if (p.stats && lane == 0) {
+        long long* o = p.stats + ((size_t)blockIdx.x * 8 + warp) * 8;
+        o[0] = clock64() - st0; o[1] = st_w; o[2] = st_start;
+    }
 }
 
 template <int CPL, int K>
@@ -633,6 +720,7 @@ unsigned* launch_tone_bf(const ToneFbArgs& a, void* ws, unsigned* counter, cudaS
     p.GT = p.A + (size_t)a.batch_size * 2 * p.nrows * RS;
     p.status = (unsigned*)(p.GT + (size_t)a.batch_size * 2 * kTWarps * RW);
     p.counter = counter;
+    p.stats = fb_get_stats_buffer();
     const size_t slot_bytes = ((size_t)3 * kSR * RW + 32) * sizeof(float);
     int NS = (int)((size_t)(224 * 1024 - kTHeader) / slot_bytes);
     NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);
