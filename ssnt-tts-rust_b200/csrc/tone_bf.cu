@@ -393,9 +393,15 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Gradient CTA.  Lane ownership is TOKEN-STRIDED here: lane l owns the tokens u = q*32 + l (q < CPL), each a
+// float4 of K = 4 tones, so every access to the [.., U, K] tensors is one fully coalesced 512-byte request per
+// instruction (the recursion's "CPL consecutive tokens per lane" would touch 16 lines per instruction).  The
+// scratch rows are in the recursion's interleaved layout: token u sits at float4 (u % CPL)*32 + u / CPL and
+// carries the exponent of recursion lane u / CPL.
 template <int CPL, int K>
 __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U, unsigned char* smem_raw) {
-    constexpr int W = CPL * K, RW = 32 * W, RS = RW + 32;
+    static_assert(K == 4, "one float4 per token");
+    constexpr int RW = 32 * CPL * K, RS = RW + 32;
     constexpr int ROWS = 16;  // rows per published round
     const ToneFbArgs& a = p.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -403,62 +409,78 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
     const int m = (T + 1) >> 1;
     const int n1 = d == 0 ? m - 1 : T - m + 1;
     const size_t slab = (size_t)a.max_t * RW;
-    const float* le = a.log_emit + (size_t)b * slab;
-    const float* ls = a.log_shift + (size_t)b * slab;
-    const float* lt = a.log_tone + (size_t)b * RW;
-    float* ge = a.grad_emit + (size_t)b * slab;
-    float* gs = a.grad_shift + (size_t)b * slab;
+    const float4* le = reinterpret_cast<const float4*>(a.log_emit + (size_t)b * slab);
+    const float4* ls = reinterpret_cast<const float4*>(a.log_shift + (size_t)b * slab);
+    const float4* lt = reinterpret_cast<const float4*>(a.log_tone + (size_t)b * RW);
+    float4* ge = reinterpret_cast<float4*>(a.grad_emit + (size_t)b * slab);
+    float4* gs = reinterpret_cast<float4*>(a.grad_shift + (size_t)b * slab);
     const float* A0 = p.A + ((size_t)b * 2 + 0) * (size_t)p.nrows * RS;  // row j = alpha(j)
     const float* A1 = p.A + ((size_t)b * 2 + 1) * (size_t)p.nrows * RS;  // row j = beta(T - j)
-    float* GT = p.GT + (((size_t)b * 2 + d) * kTWarps + warp) * RW;
+    float4* GT = reinterpret_cast<float4*>(p.GT + (((size_t)b * 2 + d) * kTWarps + warp) * RW);
     const int* round_done = reinterpret_cast<const int*>(smem_raw + 1024);
     int* ll_flag = reinterpret_cast<int*>(smem_raw + 704);
     float* llinfo = reinterpret_cast<float*>(smem_raw + 720);
-    const int f0 = lane * W;
+    constexpr int R4 = RW / 4;  // float4s per row (= tokens)
 
     auto rows_ready = [&](int dd, int n) {
         if (n <= 0) return true;
         const int r = (n - 1) / ROWS;
         return flag_load(round_done + dd * kRoundRing + (r % kRoundRing)) >= r + 1;
     };
-    float tone[W], gacc[W];
-    {
-        float raw[W];
-        ld_row<W>(lt + f0, raw);
-#pragma unroll
-        for (int i = 0; i < W; ++i) {
-            tone[i] = (lane * CPL + i / K < U) ? ex2(raw[i] * kLog2e) : 0.0f;
-            gacc[i] = 0.0f;
-        }
-    }
+    auto ready = [&](int jj) { return rows_ready(d, jj + 1) && rows_ready(1 - d, T - jj); };
+
+    int apos[CPL], alane[CPL];  // where this lane's tokens sit in a scratch row / whose exponent they carry
     bool me[CPL], ms[CPL];
+    float4 tone[CPL], gacc[CPL];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-        me[i] = lane * CPL + i < U;
-        ms[i] = lane * CPL + i < U - 1;
+    for (int q = 0; q < CPL; ++q) {
+        const int u = q * 32 + lane;
+        apos[q] = (u % CPL) * 32 + u / CPL;
+        alane[q] = u / CPL;
+        me[q] = u < U;
+        ms[q] = u < U - 1;
+        const float4 r = lt[u];
+        tone[q] = me[q] ? make_float4(ex2(r.x * kLog2e), ex2(r.y * kLog2e), ex2(r.z * kLog2e), ex2(r.w * kLog2e))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        gacc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float f_inv_sum = 0.0f;
     int f_M = 0;
     bool f_dead = false, have_ll = false;
-
-    // one sweep row per work unit; warp w takes the rows n1 + w, n1 + w + 8, ...  The next row's loads are
-    // issued before the current row is computed (two register sets): a row's inputs come from L2/HBM
-    // (~2-3 k cycles) and eight warps with one row in flight each cannot hide that.
     const long long st0 = p.stats ? clock64() : 0;
     long long st_w = 0, st_start = 0;
-    auto ready = [&](int jj) { return rows_ready(d, jj + 1) && rows_ready(1 - d, T - jj); };
-    auto load = [&](int jj, float (&E)[W], float (&S)[W], float (&VA)[W], float (&VB)[W], int& exA, int& exB) {
+
+    struct Row {
+        float4 E[CPL], S[CPL], VA[CPL], VB[CPL];
+        int exA[CPL], exB[CPL];
+    };
+    auto load = [&](int jj, Row& r) {
         const int t = dir > 0 ? jj : T - 1 - jj;
         const float* arow = A0 + (size_t)t * RS;            // alpha(t)
         const float* brow = A1 + (size_t)(T - 1 - t) * RS;  // beta(t+1)
-        ldcg_row<W>(le + (size_t)t * RW + f0, E);
-        ldcg_row<W>(ls + (size_t)t * RW + f0, S);
-        ldcgp_row<W>(arow, lane, VA);
-        ldcgp_row<W>(brow, lane, VB);
-        exA = __ldcg(reinterpret_cast<const int*>(arow) + RW + lane);
-        exB = __ldcg(reinterpret_cast<const int*>(brow) + RW + lane);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            r.E[q] = __ldcg(le + (size_t)t * R4 + q * 32 + lane);
+            r.S[q] = __ldcg(ls + (size_t)t * R4 + q * 32 + lane);
+            r.VA[q] = __ldcg(reinterpret_cast<const float4*>(arow) + apos[q]);
+            r.VB[q] = __ldcg(reinterpret_cast<const float4*>(brow) + apos[q]);
+            r.exA[q] = __ldcg(reinterpret_cast<const int*>(arow) + RW + alane[q]);
+            r.exB[q] = __ldcg(reinterpret_cast<const int*>(brow) + RW + alane[q]);
+        }
     };
-    auto compute = [&](int j, float (&E)[W], float (&S)[W], float (&VA)[W], float (&VB)[W], const int exA, const int exB) {
+    auto prefetch_row = [&](int jj) {
+        if (jj >= T) return;
+        const int t = dir > 0 ? jj : T - 1 - jj;
+        const float* src[4] = {reinterpret_cast<const float*>(le + (size_t)t * R4), reinterpret_cast<const float*>(ls + (size_t)t * R4),
+                               A0 + (size_t)t * RS, A1 + (size_t)(T - 1 - t) * RS};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int nl = (r < 2 ? RW : RS) / 32 + (r < 2 ? 0 : 1);
+            if (lane < nl) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[r] + lane * 32));
+        }
+    };
+    auto dot4 = [](const float4& x, const float4& y) { return fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, x.w * y.w))); };
+    auto compute = [&](int j, Row& r) {
         const int t = dir > 0 ? j : T - 1 - j;
         const bool ll_producer = d == 0 && j == n1;
         if (!have_ll && !ll_producer) {
@@ -470,45 +492,56 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
             have_ll = true;
         }
         const bool not_last = t != T - 1;
-#pragma unroll
-        for (int i = 0; i < W; ++i) {
-            E[i] = me[i / K] ? ex2(E[i] * kLog2e) : 0.0f;
-            S[i] = (ms[i / K] && not_last) ? ex2(S[i] * kLog2e) : 0.0f;
-        }
-        // Y(t+1, u) = sum_k tone(u,k) beta(t+1,u,k) per token; the last token needs lane+1's first
         float Y[CPL], X[CPL];
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            float y = 0.0f, x = 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < K; ++kk) {
-                y = fmaf(tone[i * K + kk], VB[i * K + kk], y);
-                x = fmaf(VA[i * K + kk], S[i * K + kk], x);  // X(t,u) = sum_k alpha(t,u,k) s(t,u,k)
-            }
-            Y[i] = y;
-            X[i] = x;
+        for (int q = 0; q < CPL; ++q) {
+            float4& E = r.E[q];
+            float4& S = r.S[q];
+            if (me[q]) E = make_float4(ex2(E.x * kLog2e), ex2(E.y * kLog2e), ex2(E.z * kLog2e), ex2(E.w * kLog2e));
+            else E = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ms[q] && not_last) S = make_float4(ex2(S.x * kLog2e), ex2(S.y * kLog2e), ex2(S.z * kLog2e), ex2(S.w * kLog2e));
+            else S = make_float4(0.f, 0.f, 0.f, 0.f);
+            Y[q] = dot4(tone[q], r.VB[q]);  // Y(t+1, u) = sum_k tone(u,k) beta(t+1,u,k)
+            X[q] = dot4(r.VA[q], S);        // X(t, u)   = sum_k alpha(t,u,k) s(t,u,k)
         }
-        const int exBn = __shfl_down_sync(kFull, exB, 1);
-        float y_edge = scale_pow2(__shfl_down_sync(kFull, Y[0], 1), exBn - exB);
-        if (lane == 31) y_edge = 0.0f;
-        const int exAp = __shfl_up_sync(kFull, exA, 1);
-        float x_edge = scale_pow2(__shfl_up_sync(kFull, X[CPL - 1], 1), exAp - exA);  // X(t, c0-1) in this lane's alpha frame
-        if (lane == 0) x_edge = 0.0f;
-        const int EL = exA + exB;
+        // neighbours: token u+1 is lane+1 (same q) or lane 0 of q+1; token u-1 is lane-1 or lane 31 of q-1;
+        // both re-framed into this token's exponents
+        float yn[CPL], xp[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            float y = __shfl_down_sync(kFull, Y[q], 1);
+            int ey = __shfl_down_sync(kFull, r.exB[q], 1);
+            const float y0 = q + 1 < CPL ? __shfl_sync(kFull, Y[q + 1 < CPL ? q + 1 : q], 0) : 0.0f;
+            const int ey0 = q + 1 < CPL ? __shfl_sync(kFull, r.exB[q + 1 < CPL ? q + 1 : q], 0) : 0;
+            if (lane == 31) { y = y0; ey = ey0; }
+            yn[q] = (q + 1 < CPL || lane < 31) ? scale_pow2(y, ey - r.exB[q]) : 0.0f;
+            float x = __shfl_up_sync(kFull, X[q], 1);
+            int exx = __shfl_up_sync(kFull, r.exA[q], 1);
+            const float x31 = q > 0 ? __shfl_sync(kFull, X[q > 0 ? q - 1 : q], 31) : 0.0f;
+            const int ex31 = q > 0 ? __shfl_sync(kFull, r.exA[q > 0 ? q - 1 : q], 31) : 0;
+            if (lane == 0) { x = x31; exx = ex31; }
+            xp[q] = (q > 0 || lane > 0) ? scale_pow2(x, exx - r.exA[q]) : 0.0f;
+        }
         if (ll_producer) {
-            float w = 0.0f;
+            // Z = sum_{u,k} alpha(m-1,u,k) (e beta(m,u,k) + s Y(m,u+1)), tokens carry different exponents
+            float w[CPL];
+            int key = kNoMass;
+            bool finite = true;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const float yn = (i + 1 < CPL) ? Y[i + 1] : y_edge;
-#pragma unroll
-                for (int kk = 0; kk < K; ++kk)
-                    w += VA[i * K + kk] * (E[i * K + kk] * VB[i * K + kk] + S[i * K + kk] * yn);
+            for (int q = 0; q < CPL; ++q) {
+                const float4 &E = r.E[q], &S = r.S[q], &VA = r.VA[q], &VB = r.VB[q];
+                w[q] = VA.x * (E.x * VB.x + S.x * yn[q]) + VA.y * (E.y * VB.y + S.y * yn[q]) +
+                       VA.z * (E.z * VB.z + S.z * yn[q]) + VA.w * (E.w * VB.w + S.w * yn[q]);
+                finite = finite && (w[q] == w[q] && w[q] < 3.0e38f);
+                if (w[q] > 0.0f && w[q] < 3.0e38f) key = max(key, r.exA[q] + r.exB[q] + ilogb_pos(w[q]));
             }
-            const bool finite = w == w && w < 3.0e38f;
-            int M = (finite && w > 0.0f) ? EL + ilogb_pos(w) : kNoMass;
+            int M = key;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) M = max(M, __shfl_xor_sync(kFull, M, o));
-            const float part = (finite && w > 0.0f) ? scale_pow2(w, EL - M) : 0.0f;
+            float part = 0.0f;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q)
+                if (w[q] > 0.0f && w[q] < 3.0e38f) part += scale_pow2(w[q], r.exA[q] + r.exB[q] - M);
             const float sum = warp_sum(part);
             const unsigned bad = __ballot_sync(kFull, !finite);
             unsigned st = 0;
@@ -535,53 +568,37 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
                 asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(rf), "r"(1) : "memory");
             }
         }
-        const int kf = max(-252, min(252, EL - f_M));
-        const int kh = kf >> 1;
-        const float fa = pow2i(max(-126, kh));
-        const float fb = pow2i(max(-126, kf - kh)) * f_inv_sum;
-        float g1[W], g2[W];
-        float occ0 = 0.0f, occT = 0.0f;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            const float yn = (i + 1 < CPL) ? Y[i + 1] : y_edge;
-            const float xp = (i > 0) ? X[i - 1] : x_edge;  // X(t, u-1): mass that enters token u at frame t+1
-#pragma unroll
-            for (int kk = 0; kk < K; ++kk) {
-                const int q = i * K + kk;
-                const float va = VA[q] * fa;
-                g1[q] = f_dead ? 0.0f : va * ((E[q] * VB[q]) * fb);
-                g2[q] = f_dead ? 0.0f : va * ((S[q] * yn) * fb);
-                // d LL / d log_tone(u,k): entering token u with tone k at frame t+1
-                if (!f_dead) gacc[q] += (xp * fa) * ((tone[q] * VB[q]) * fb);
-                if (lane == 0 && i == 0) occ0 += g1[q] + g2[q];
-                if (lane * CPL + i == U - 1) occT += g1[q];
+        for (int q = 0; q < CPL; ++q) {
+            const int u = q * 32 + lane;
+            const int kf = max(-252, min(252, r.exA[q] + r.exB[q] - f_M));
+            const int kh = kf >> 1;
+            const float fa = pow2i(max(-126, kh));
+            const float fb = pow2i(max(-126, kf - kh)) * f_inv_sum;
+            const float4 &E = r.E[q], &S = r.S[q], &VA = r.VA[q], &VB = r.VB[q];
+            const float4 va = make_float4(VA.x * fa, VA.y * fa, VA.z * fa, VA.w * fa);
+            float4 g1 = make_float4(va.x * ((E.x * VB.x) * fb), va.y * ((E.y * VB.y) * fb), va.z * ((E.z * VB.z) * fb), va.w * ((E.w * VB.w) * fb));
+            const float sy = yn[q] * fb;
+            float4 g2 = make_float4(va.x * (S.x * sy), va.y * (S.y * sy), va.z * (S.z * sy), va.w * (S.w * sy));
+            if (f_dead) { g1 = make_float4(0.f, 0.f, 0.f, 0.f); g2 = g1; }
+            __stcs(ge + (size_t)t * R4 + u, g1);
+            __stcs(gs + (size_t)t * R4 + u, g2);
+            if (!f_dead) {
+                // d LL / d log_tone(u,k): entering token u with tone k at frame t+1 (X(t,u-1) tone beta / Z) ...
+                const float xf = xp[q] * fa;
+                gacc[q].x += xf * ((tone[q].x * VB.x) * fb);
+                gacc[q].y += xf * ((tone[q].y * VB.y) * fb);
+                gacc[q].z += xf * ((tone[q].z * VB.z) * fb);
+                gacc[q].w += xf * ((tone[q].w * VB.w) * fb);
+                if (t == 0 && u == 0) {  // ... and token 0 draws its tone at the start: occupancy of (0, 0, k)
+                    gacc[q].x += g1.x + g2.x; gacc[q].y += g1.y + g2.y; gacc[q].z += g1.z + g2.z; gacc[q].w += g1.w + g2.w;
+                }
+                bool bad = false;
+                if (d == 0 && t == T - 1 && u == U - 1) bad = !(fabsf(g1.x + g1.y + g1.z + g1.w - 1.0f) < kBfConsistency);
+                if (d == 1 && t == 0 && u == 0)
+                    bad = !(fabsf(g1.x + g1.y + g1.z + g1.w + g2.x + g2.y + g2.z + g2.w - 1.0f) < kBfConsistency);
+                if (bad) atomicOr(p.status + b, (unsigned)kBfInconsistent);
             }
-        }
-        stcs_row<W>(ge + (size_t)t * RW + f0, g1);
-        stcs_row<W>(gs + (size_t)t * RW + f0, g2);
-        if (t == 0 && !f_dead && lane == 0) {
-            // token 0 draws its tone at the start: occupancy of (0, 0, k)
-#pragma unroll
-            for (int kk = 0; kk < K; ++kk) gacc[kk] += g1[kk] + g2[kk];
-        }
-        if (!f_dead && (t == T - 1 || t == 0)) {
-            bool bad = false;
-            if (d == 0 && t == T - 1 && (U - 1) / CPL == lane) bad = !(fabsf(occT - 1.0f) < kBfConsistency);
-            if (d == 1 && t == 0 && lane == 0) bad = !(fabsf(occ0 - 1.0f) < kBfConsistency);
-            if (bad) atomicOr(p.status + b, (unsigned)kBfInconsistent);
-        }
-    };
-    // L2 prefetch of a future row's four inputs (2 KB each): 17 lines per array, 64 lines over 32 lanes x 2.
-    // The working set (inputs 105 MB + scratch rows 111 MB at config 3) does not live in L2, so without this
-    // every row pays an HBM round trip with only two rows in flight per warp.
-    auto prefetch_row = [&](int jj) {
-        if (jj >= T) return;
-        const int t = dir > 0 ? jj : T - 1 - jj;
-        const float* src[4] = {le + (size_t)t * RW, ls + (size_t)t * RW, A0 + (size_t)t * RS, A1 + (size_t)(T - 1 - t) * RS};
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int nl = (r < 2 ? RW : RS) / 32 + (r < 2 ? 0 : 1);
-            if (lane < nl) asm volatile("prefetch.global.L2 [%0];" ::"l"(src[r] + lane * 32));
         }
     };
     auto wait_ready = [&](int jj) {
@@ -590,31 +607,33 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
         if (p.stats) { const long long t1 = clock64(); st_w += t1 - tw0; if (!st_start) st_start = t1 - st0; }
     };
     {
-        float EA[W], SA[W], VAA[W], VBA[W], EB[W], SB[W], VAB[W], VBB[W];
-        int xAA = 0, xBA = 0, xAB = 0, xBB = 0;
+        // one sweep row per work unit; warp w takes the rows n1 + w, n1 + w + 8, ...; the next row's loads are
+        // issued before the current row is computed (two register sets) and L2 prefetches run further ahead
+        Row ra, rb;
         bool hasA = false, hasB = false;
         int j = n1 + warp;
-        constexpr int kAhead = 4;  // prefetch distance in this warp's own rows (x8 sweep rows)
+        constexpr int kAhead = 4;
         for (int q = 1; q <= kAhead; ++q) prefetch_row(j + q * kTWarps);
         while (j < T) {
             prefetch_row(j + (kAhead + 1) * kTWarps);
             prefetch_row(j + (kAhead + 2) * kTWarps);
-            if (!hasA) { wait_ready(j); load(j, EA, SA, VAA, VBA, xAA, xBA); }
+            if (!hasA) { wait_ready(j); load(j, ra); }
             hasA = false;
             const int j2 = j + kTWarps;
-            if (j2 < T && ready(j2)) { load(j2, EB, SB, VAB, VBB, xAB, xBB); hasB = true; }
-            compute(j, EA, SA, VAA, VBA, xAA, xBA);
+            if (j2 < T && ready(j2)) { load(j2, rb); hasB = true; }
+            compute(j, ra);
             j = j2;
             if (j >= T) break;
-            if (!hasB) { wait_ready(j); load(j, EB, SB, VAB, VBB, xAB, xBB); }
+            if (!hasB) { wait_ready(j); load(j, rb); }
             hasB = false;
             const int j3 = j + kTWarps;
-            if (j3 < T && ready(j3)) { load(j3, EA, SA, VAA, VBA, xAA, xBA); hasA = true; }
-            compute(j, EB, SB, VAB, VBB, xAB, xBB);
+            if (j3 < T && ready(j3)) { load(j3, ra); hasA = true; }
+            compute(j, rb);
             j = j3;
         }
     }
-    st_row<W>(GT + f0, gacc);
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) GT[q * 32 + lane] = gacc[q];
     if (p.stats && lane == 0) {
         long long* o = p.stats + ((size_t)blockIdx.x * 8 + warp) * 8;
         o[0] = clock64() - st0; o[1] = st_w; o[2] = st_start;
