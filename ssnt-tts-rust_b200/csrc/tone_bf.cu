@@ -101,7 +101,13 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
     constexpr int W = CPL * K;              // floats of a row owned by one lane
     constexpr int RW = 32 * W;              // floats of a row
     constexpr int RS = RW + 32;             // scratch row stride (lane exponents behind the row)
-    constexpr int slot_floats = 3 * kSR * RW + 32;
+    // e/s rows in the ring: token u (recursion lane u/CPL, its (u%CPL)-th float4) at float4 (u%CPL)*S4 + u/CPL.
+    // S4 = 32 + 8/CPL makes BOTH the recursion's reads (a lane's q-th float4, lanes consecutive) and the prep
+    // warps' token-strided writes (lanes walk u) conflict-free; the state rows keep stride 32.
+    constexpr int S4 = CPL == 1 ? 32 : 32 + 8 / CPL;
+    constexpr int RWP = CPL * S4 * 4;       // floats of a padded e/s row
+    constexpr int slot_floats = 2 * kSR * RWP + kSR * RW + 32;
+    constexpr int off_s = kSR * RWP, off_v = 2 * kSR * RWP, off_x = 2 * kSR * RWP + kSR * RW;
     const ToneFbArgs& a = p.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NS = p.NS, dir = d == 0 ? 1 : -1;
@@ -117,6 +123,13 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
     float* ringm = reinterpret_cast<float*>(smem_raw + kTHeader);
     auto slot_ptr = [&](int slot) { return ringm + (size_t)slot * slot_floats; };
     const int f0 = lane * W;                // first float of this lane inside a row
+    auto ldpp = [&](const float* row, float (&x)[W]) {  // this lane's CPL float4s of a padded e/s row
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(row + (q * S4 + lane) * 4);
+            x[4 * q] = w.x; x[4 * q + 1] = w.y; x[4 * q + 2] = w.z; x[4 * q + 3] = w.w;
+        }
+    };
     const bool is_copy = warp == 4 || warp == 7;
     const int copy_idx = warp == 4 ? 0 : 1;
     const int prep_idx = warp - 1 - (warp > 4 ? 1 : 0);  // warps 1,2,3,5,6 → 0..4
@@ -197,15 +210,15 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
             }
             int own = kNoMass, nbmag = kNoMass;
             for (int z = 0; z < ns; ++z)
-                reinterpret_cast<int*>(slot_ptr((slot0 + z) & (NS - 1)) + 3 * kSR * RW)[lane] = ex;
+                reinterpret_cast<int*>(slot_ptr((slot0 + z) & (NS - 1)) + off_x)[lane] = ex;
             // rows of the round, the next row's probabilities requested before the current row is computed
             // (the compiler cannot hoist those loads itself: they might alias the state rows stored in between)
             const int nrow = ns * kSR;
             float E[2][W], S[2][W];
             {
                 const float* sp0 = slot_ptr(slot0);
-                ldp_row<W>(sp0, lane, E[0]);
-                ldp_row<W>(sp0 + kSR * RW, lane, S[0]);
+                ldpp(sp0, E[0]);
+                ldpp(sp0 + off_s, S[0]);
             }
 #pragma unroll 2
             for (int r = 0; r < nrow; ++r) {
@@ -215,10 +228,10 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 if (r + 1 < nrow) {
                     const float* spn = slot_ptr((slot0 + ((r + 1) >> 2)) & (NS - 1));
                     const int qn = (r + 1) & (kSR - 1);
-                    if (cb == 0) { ldp_row<W>(spn + qn * RW, lane, E[1]); ldp_row<W>(spn + (kSR + qn) * RW, lane, S[1]); }
-                    else { ldp_row<W>(spn + qn * RW, lane, E[0]); ldp_row<W>(spn + (kSR + qn) * RW, lane, S[0]); }
+                    if (cb == 0) { ldpp(spn + qn * RWP, E[1]); ldpp(spn + off_s + qn * RWP, S[1]); }
+                    else { ldpp(spn + qn * RWP, E[0]); ldpp(spn + off_s + qn * RWP, S[0]); }
                 }
-                stp_row<W>(sp + (2 * kSR + q) * RW, lane, v);  // the state BEFORE the step is this row
+                stp_row<W>(sp + off_v + q * RW, lane, v);  // the state BEFORE the step is this row
                 auto step = [&](const float (&Ec)[W], const float (&Sc)[W]) {
                     if (d == 0) {
                         float X[CPL];
@@ -297,11 +310,18 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
         }
     } else if (!is_copy) {
         // ------------------------------- prep -------------------------------
+        // token-strided ownership (lane l: tokens q*32 + l, one float4 of K tones each): coalesced global loads
+        const float4* le4 = reinterpret_cast<const float4*>(le);
+        const float4* ls4 = reinterpret_cast<const float4*>(ls);
+        constexpr int R4 = RW / 4;
         bool me[CPL], ms[CPL];
+        int ppos[CPL];
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-            me[i] = lane * CPL + i < U;
-            ms[i] = lane * CPL + i < U - 1;
+        for (int q = 0; q < CPL; ++q) {
+            const int u = q * 32 + lane;
+            me[q] = u < U;
+            ms[q] = u < U - 1;
+            ppos[q] = ((u % CPL) * S4 + u / CPL) * 4;
         }
         const long long st0 = p.stats ? clock64() : 0;
         long long st_w = 0;
@@ -319,17 +339,20 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                     }
                 }
             }
-            float RE[kSR][W], RSv[kSR][W];
+            float4 RE[kSR][CPL], RSv[kSR][CPL];
 #pragma unroll
             for (int q = 0; q < kSR; ++q) {
                 const int j = k * kSR + q;
                 const int t = dir > 0 ? j : T - 1 - j;
-                if (j < T) {
-                    ldcg_row<W>(le + (size_t)t * RW + f0, RE[q]);
-                    ldcg_row<W>(ls + (size_t)t * RW + f0, RSv[q]);
-                } else {
 #pragma unroll
-                    for (int i = 0; i < W; ++i) { RE[q][i] = -INFINITY; RSv[q][i] = -INFINITY; }
+                for (int c = 0; c < CPL; ++c) {
+                    if (j < T) {
+                        RE[q][c] = __ldcg(le4 + (size_t)t * R4 + c * 32 + lane);
+                        RSv[q][c] = __ldcg(ls4 + (size_t)t * R4 + c * 32 + lane);
+                    } else {
+                        RE[q][c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        RSv[q][c] = RE[q][c];
+                    }
                 }
             }
 #pragma unroll
@@ -338,21 +361,27 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 const int t = dir > 0 ? j : T - 1 - j;
                 const bool not_last = t != T - 1;
 #pragma unroll
-                for (int i = 0; i < W; ++i) {
-                    RE[q][i] = me[i / K] ? ex2(RE[q][i] * kLog2e) : 0.0f;
-                    RSv[q][i] = (ms[i / K] && not_last) ? ex2(RSv[q][i] * kLog2e) : 0.0f;
+                for (int c = 0; c < CPL; ++c) {
+                    float4& E = RE[q][c];
+                    float4& S = RSv[q][c];
+                    if (me[c]) E = make_float4(ex2(E.x * kLog2e), ex2(E.y * kLog2e), ex2(E.z * kLog2e), ex2(E.w * kLog2e));
+                    else E = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ms[c] && not_last) S = make_float4(ex2(S.x * kLog2e), ex2(S.y * kLog2e), ex2(S.z * kLog2e), ex2(S.w * kLog2e));
+                    else S = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            // the slot's e/s region is free once the recursion has consumed its previous occupant
             { const long long t0 = p.stats ? clock64() : 0;
+              // the slot's e/s region is free once the recursion has consumed its previous occupant
               if (k >= NS) wait_flag_ge(state_done + slot, k / NS, 128);
               if (p.stats) st_w += clock64() - t0; }
             float* dst = slot_ptr(slot);
 #pragma unroll
-            for (int q = 0; q < kSR; ++q) {
-                stp_row<W>(dst + q * RW, lane, RE[q]);
-                stp_row<W>(dst + (kSR + q) * RW, lane, RSv[q]);
-            }
+            for (int q = 0; q < kSR; ++q)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    *reinterpret_cast<float4*>(dst + q * RWP + ppos[c]) = RE[q][c];
+                    *reinterpret_cast<float4*>(dst + off_s + q * RWP + ppos[c]) = RSv[q][c];
+                }
             __syncwarp();
             if (lane == 0) flag_publish(ready + slot, k / NS + 1);
         }
@@ -370,11 +399,11 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 const int slot = k & (NS - 1);
                 wait_flag_ge(state_done + slot, k / NS + 1, 128);
                 const float* sp = slot_ptr(slot);
-                const int exs = reinterpret_cast<const int*>(sp + 3 * kSR * RW)[lane];
+                const int exs = reinterpret_cast<const int*>(sp + off_x)[lane];
 #pragma unroll
                 for (int q = 0; q < kSR; ++q) {
                     float x[W];
-                    ldp_row<W>(sp + (2 * kSR + q) * RW, lane, x);
+                    ldp_row<W>(sp + off_v + q * RW, lane, x);
                     float* dst = Ad + (size_t)(k * kSR + q) * RS;
                     stp_row<W>(dst, lane, x);  // the scratch rows keep the interleaved layout
                     reinterpret_cast<int*>(dst)[RW + lane] = exs;
@@ -740,7 +769,9 @@ unsigned* launch_tone_bf(const ToneFbArgs& a, void* ws, unsigned* counter, cudaS
     p.status = (unsigned*)(p.GT + (size_t)a.batch_size * 2 * kTWarps * RW);
     p.counter = counter;
     p.stats = fb_get_stats_buffer();
-    const size_t slot_bytes = ((size_t)3 * kSR * RW + 32) * sizeof(float);
+    const int cpl = a.max_u / 32;
+    const size_t RWP = (size_t)cpl * (cpl == 1 ? 32 : 32 + 8 / cpl) * 4;  // padded e/s row, see tone_chain_cta
+    const size_t slot_bytes = ((size_t)2 * kSR * RWP + (size_t)kSR * RW + 32) * sizeof(float);
     int NS = (int)((size_t)(224 * 1024 - kTHeader) / slot_bytes);
     NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);
     p.NS = NS;
