@@ -25,8 +25,8 @@ constexpr int kTThreads = 256;
 constexpr int kTWarps = 8;
 constexpr int kSR = 4;            // rows per stage
 constexpr int kTHeader = 2048;
-constexpr int kTPrepWarps = 5;    // warps 1,2,3,5,6 (sub-partitions 1-3); 4 and 7: copy-out
-constexpr int kTCopyWarps = 2;
+constexpr int kTPrepWarps = 4;    // warps 1,2,3,5 (sub-partitions 1-3)
+constexpr int kTCopyWarps = 3;    // warps 4,6,7
 
 struct ToneBfParams {
     ToneFbArgs a;
@@ -130,9 +130,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
             x[4 * q] = w.x; x[4 * q + 1] = w.y; x[4 * q + 2] = w.z; x[4 * q + 3] = w.w;
         }
     };
-    const bool is_copy = warp == 4 || warp == 7;
-    const int copy_idx = warp == 4 ? 0 : 1;
-    const int prep_idx = warp - 1 - (warp > 4 ? 1 : 0);  // warps 1,2,3,5,6 → 0..4
+    const bool is_copy = warp == 4 || warp >= 6;
+    const int copy_idx = warp == 4 ? 0 : warp - 5;        // warps 4,6,7 → 0,1,2
+    const int prep_idx = warp - 1 - (warp > 4 ? 1 : 0);  // warps 1,2,3,5 → 0..3
 
     if (warp == 0) {
         // ------------------------------- recursion -------------------------------
