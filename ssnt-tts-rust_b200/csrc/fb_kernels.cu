@@ -443,7 +443,7 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         if (const char* e = std::getenv("SSNT_SPLIT_DEBUG")) p.debug = std::atoi(e);  // profiling aid
         p.counter = counter;
         p.stats = tls_stats;
-        const size_t slot_bytes = ((size_t)3 * kG * a.max_u + 32) * sizeof(float);
+        const size_t slot_bytes = ((size_t)2 * kG * a.max_u) * sizeof(float);
         int NS = (int)((size_t)(224 * 1024 - kSplitHeaderBytes) / slot_bytes);
         NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);  // power of two (the recursion indexes the ring with masks)
         SSNT_ASSERT((size_t)NS * slot_bytes + kSplitHeaderBytes <= 224 * 1024, "forward_backward: ring does not fit shared memory");

@@ -93,8 +93,9 @@ __device__ __forceinline__ void ldcg_cells(const float* row, int c0, float (&v)[
 // probability feeding its first cell and those between its cells.
 template <int CPL, int RANK, int NSTG, typename H1, typename H2>
 __device__ __forceinline__ void chain_round_split(ChainState<CPL>& cs, const float g, float* const (&sp)[4],
-                                                  const int lane, H1 h1, H2 h2) {
+                                                  const int lane, H1 h1, H2 h2, float* grow, const int ex) {
     constexpr int max_u = 32 * CPL;
+    constexpr int SU = max_u + 32;
     constexpr int NR = NSTG * kG;
     constexpr int CH = CPL <= 4 ? 4 : 2;  // rows per chunk (register budget)
     constexpr int NC = NR / CH;
@@ -126,7 +127,12 @@ __device__ __forceinline__ void chain_round_split(ChainState<CPL>& cs, const flo
             } else {
                 skew_step<CPL, 1>(cs, E[c & 1][r], S[c & 1][r], 0.0f, g, out);
             }
-            store_cells<CPL>(sp[q >> 3] + (2 * kG + (q & 7)) * max_u, c0, max_u, out);
+            // the state row goes straight to the global scratch (values + this lane's exponent): keeping it in
+            // the ring for a copy-out warp costs a shared store here plus a shared load there, and the
+            // recursion SM is bound by its shared-memory pipe
+            float* dst = grow + q * SU;
+            store_cells<CPL>(dst, c0, max_u, out);
+            if ((q & 7) == 0) reinterpret_cast<int*>(dst)[max_u + lane] = ex;  // one exponent row per stage (rounds start at stage boundaries)
             if (q == NR - 3) h1();
             if (q == NR - 2) h2();
         }
@@ -140,7 +146,7 @@ template <int CPL>
 __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int T, int U, unsigned char* smem_raw) {
     constexpr int max_u = 32 * CPL, SU = max_u + 32;
     constexpr int stageP = 2 * kG * max_u;                     // floats of one probability stage
-    constexpr int slot_floats = stageP + kG * max_u + 32;      // e | s | state rows | lane exponents
+    constexpr int slot_floats = stageP;                        // e | s
     const FbArgs& a = p.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NS = p.NS;
@@ -251,22 +257,20 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
 #pragma unroll
             for (int z = 0; z < 4; ++z) sp[z] = slot_ptr((slot0 + z) & (NS - 1));
             if (!(p.debug & 1)) apply_decision();
-#pragma unroll
-            for (int z = 0; z < 4; ++z)
-                if (z < ns) reinterpret_cast<int*>(sp[z] + stageP + kG * max_u)[lane] = ex;
             int own = kNoMass, nbmag = kNoMass;
             auto d1 = [&]() { if (!(p.debug & 2)) decide_1(own, nbmag); };
             auto d2 = [&]() { if (!(p.debug & 2)) decide_2(own, nbmag); };
+            float* grow = Ad + (size_t)k * kG * SU;  // scratch row of the round's first lattice row (sweep order)
             const long long tr1 = p.stats ? clock64() : 0;
             st_mid += tr1 - tm0;
             if (d == 0) {
-                if (ns == 4) chain_round_split<CPL, 0, 4>(cs, g, sp, lane, d1, d2);
-                else if (ns == 2) chain_round_split<CPL, 0, 2>(cs, g, sp, lane, d1, d2);
-                else chain_round_split<CPL, 0, 1>(cs, g, sp, lane, d1, d2);
+                if (ns == 4) chain_round_split<CPL, 0, 4>(cs, g, sp, lane, d1, d2, grow, ex);
+                else if (ns == 2) chain_round_split<CPL, 0, 2>(cs, g, sp, lane, d1, d2, grow, ex);
+                else chain_round_split<CPL, 0, 1>(cs, g, sp, lane, d1, d2, grow, ex);
             } else {
-                if (ns == 4) chain_round_split<CPL, 1, 4>(cs, g, sp, lane, d1, d2);
-                else if (ns == 2) chain_round_split<CPL, 1, 2>(cs, g, sp, lane, d1, d2);
-                else chain_round_split<CPL, 1, 1>(cs, g, sp, lane, d1, d2);
+                if (ns == 4) chain_round_split<CPL, 1, 4>(cs, g, sp, lane, d1, d2, grow, ex);
+                else if (ns == 2) chain_round_split<CPL, 1, 2>(cs, g, sp, lane, d1, d2, grow, ex);
+                else chain_round_split<CPL, 1, 1>(cs, g, sp, lane, d1, d2, grow, ex);
             }
             const long long tr2 = p.stats ? clock64() : 0;
             if (warmup) {  // forget everything the warm-up pass computed and start over
@@ -333,7 +337,7 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
             constexpr int HR = kG / 2;  // rows per half stage
             if (k >= NS) {  // the slot's previous occupant has been consumed and its state rows copied out
                 const long long t0 = p.stats ? clock64() : 0;
-                wait_flag_ge(slot_free + slot, k / NS, kPrepPollNs);
+                wait_flag_ge(state_done + slot, k / NS, kPrepPollNs);
                 if (p.stats) st_w1 += clock64() - t0;
             }
             float* dst = slot_ptr(slot);
@@ -416,12 +420,10 @@ __device__ void split_chain_cta(const SplitParams& p, int b, unsigned rank, int 
                 const long long t0 = p.stats ? clock64() : 0;
                 wait_flag_ge(state_done + slot, k / NS + 1, kCopyPollNs);
                 if (p.stats) st_w1 += clock64() - t0;
-                const float* sp = slot_ptr(slot);
-                const int exs = reinterpret_cast<const int*>(sp + stageP + kG * max_u)[lane];
-                copy_out_rows<CPL, kG, true>(sp + stageP, Ad + (size_t)k * kG * SU, (long long)SU, exs, c0, max_u, max_u, lane);
-                __syncwarp();
-                if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(slot_free + slot)), "r"(k / NS + 1) : "memory");
             }
+            // The recursion warp stored the rows itself and released them at CTA scope (fence + flag); the
+            // GPU-scope fence below, executed after observing that flag, orders them before the flags this
+            // warp writes into the gradient CTAs (causality is transitive in the PTX memory model).
             if (lane == 0) {
                 const long long t0 = p.stats ? clock64() : 0;
                 __threadfence();
@@ -526,8 +528,9 @@ __device__ void split_helper_cta(const SplitParams& p, int b, unsigned rank, int
                 ldcg_cells<CPL>(ls + (size_t)t * max_u, c0, S[r]);
                 ldcg_cells<CPL>(arow, c0, VA[r]);
                 ldcg_cells<CPL>(brow, c0, VB[r]);
-                exA[r] = __ldcg(reinterpret_cast<const int*>(arow) + max_u + lane);
-                exB[r] = __ldcg(reinterpret_cast<const int*>(brow) + max_u + lane);
+                // lane exponents: kept in the first row of each 8-row stage of the sweep that wrote the row
+                exA[r] = __ldcg(reinterpret_cast<const int*>(A0 + (size_t)(t & ~7) * SU) + max_u + lane);
+                exB[r] = __ldcg(reinterpret_cast<const int*>(A1 + (size_t)((T - 1 - t) & ~7) * SU) + max_u + lane);
             }
             float edge[GB];
             int exBn[GB];
