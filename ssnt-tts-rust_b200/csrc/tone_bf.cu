@@ -106,8 +106,8 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
     // warps' token-strided writes (lanes walk u) conflict-free; the state rows keep stride 32.
     constexpr int S4 = CPL == 1 ? 32 : 32 + 8 / CPL;
     constexpr int RWP = CPL * S4 * 4;       // floats of a padded e/s row
-    constexpr int slot_floats = 2 * kSR * RWP + kSR * RW + 32;
-    constexpr int off_s = kSR * RWP, off_v = 2 * kSR * RWP, off_x = 2 * kSR * RWP + kSR * RW;
+    constexpr int slot_floats = 2 * kSR * RWP;
+    constexpr int off_s = kSR * RWP;
     const ToneFbArgs& a = p.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NS = p.NS, dir = d == 0 ? 1 : -1;
@@ -190,14 +190,6 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(fl.x), "=r"(fl.y), "=r"(fl.z), "=r"(fl.w) : "r"(smem_u32(nflag)) : "memory");
             }
-            // the state region of these slots still holds the rows of NS stages ago until the copy-out
-            // warps have moved them (almost always long done: probe once, then poll)
-            if (use > 1) {
-                for (int z = 0; z < ns; ++z)
-                    while (!__all_sync(kFull, flag_load(slot_free + ((slot0 + z) & (NS - 1))) >= use - 1)) {
-                    }
-            }
-            if (p.stats) st_f += clock64() - tw1;
             // ---- apply the re-normalisation decided in the previous round ----
             if (have_dec) {
                 const int shift = ex - ex_dec;
@@ -209,8 +201,6 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                 have_dec = false;
             }
             int own = kNoMass, nbmag = kNoMass;
-            for (int z = 0; z < ns; ++z)
-                reinterpret_cast<int*>(slot_ptr((slot0 + z) & (NS - 1)) + off_x)[lane] = ex;
             // rows of the round, the next row's probabilities requested before the current row is computed
             // (the compiler cannot hoist those loads itself: they might alias the state rows stored in between)
             const int nrow = ns * kSR;
@@ -231,7 +221,13 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
                     if (cb == 0) { ldpp(spn + qn * RWP, E[1]); ldpp(spn + off_s + qn * RWP, S[1]); }
                     else { ldpp(spn + qn * RWP, E[0]); ldpp(spn + off_s + qn * RWP, S[0]); }
                 }
-                stp_row<W>(sp + off_v + q * RW, lane, v);  // the state BEFORE the step is this row
+                {
+                    // the state BEFORE the step is this row; it goes straight to the global scratch (interleaved
+                    // layout), with the lane exponents in the first row of each stage
+                    float* dst = Ad + (size_t)(k * kSR + r) * RS;
+                    stp_row<W>(dst, lane, v);
+                    if (q == 0) reinterpret_cast<int*>(dst)[RW + lane] = ex;
+                }
                 auto step = [&](const float (&Ec)[W], const float (&Sc)[W]) {
                     if (d == 0) {
                         float X[CPL];
@@ -395,22 +391,9 @@ __device__ void tone_chain_cta(const ToneBfParams& p, int b, int d, int T, int U
         const int nround = (nst + 3) / 4;  // publish per four stages (16 rows)
         for (int r = copy_idx; r < nround; r += kTCopyWarps) {
             const int kend = min(4 * r + 4, nst);
-            for (int k = 4 * r; k < kend; ++k) {
-                const int slot = k & (NS - 1);
-                wait_flag_ge(state_done + slot, k / NS + 1, 128);
-                const float* sp = slot_ptr(slot);
-                const int exs = reinterpret_cast<const int*>(sp + off_x)[lane];
-#pragma unroll
-                for (int q = 0; q < kSR; ++q) {
-                    float x[W];
-                    ldp_row<W>(sp + off_v + q * RW, lane, x);
-                    float* dst = Ad + (size_t)(k * kSR + q) * RS;
-                    stp_row<W>(dst, lane, x);  // the scratch rows keep the interleaved layout
-                    reinterpret_cast<int*>(dst)[RW + lane] = exs;
-                }
-                __syncwarp();
-                if (lane == 0) asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(slot_free + slot)), "r"(k / NS + 1) : "memory");
-            }
+            for (int k = 4 * r; k < kend; ++k) wait_flag_ge(state_done + (k & (NS - 1)), k / NS + 1, 128);
+            // the recursion warp stored and CTA-released the rows itself; the GPU-scope fence below, after
+            // observing its flags, orders them before the flags written into the gradient CTAs
             if (lane == 0) {
                 __threadfence();
                 const uint32_t off = 4u * (uint32_t)(d * kRoundRing + (r % kRoundRing));
@@ -493,8 +476,9 @@ __device__ void tone_grad_cta(const ToneBfParams& p, int b, int d, int T, int U,
             r.S[q] = __ldcg(ls + (size_t)t * R4 + q * 32 + lane);
             r.VA[q] = __ldcg(reinterpret_cast<const float4*>(arow) + apos[q]);
             r.VB[q] = __ldcg(reinterpret_cast<const float4*>(brow) + apos[q]);
-            r.exA[q] = __ldcg(reinterpret_cast<const int*>(arow) + RW + alane[q]);
-            r.exB[q] = __ldcg(reinterpret_cast<const int*>(brow) + RW + alane[q]);
+            // lane exponents: in the first row of the 4-row stage of the sweep that wrote the row
+            r.exA[q] = __ldcg(reinterpret_cast<const int*>(A0 + (size_t)(t & ~(kSR - 1)) * RS) + RW + alane[q]);
+            r.exB[q] = __ldcg(reinterpret_cast<const int*>(A1 + (size_t)((T - 1 - t) & ~(kSR - 1)) * RS) + RW + alane[q]);
         }
     };
     auto prefetch_row = [&](int jj) {
@@ -771,7 +755,7 @@ unsigned* launch_tone_bf(const ToneFbArgs& a, void* ws, unsigned* counter, cudaS
     p.stats = fb_get_stats_buffer();
     const int cpl = a.max_u / 32;
     const size_t RWP = (size_t)cpl * (cpl == 1 ? 32 : 32 + 8 / cpl) * 4;  // padded e/s row, see tone_chain_cta
-    const size_t slot_bytes = ((size_t)2 * kSR * RWP + (size_t)kSR * RW + 32) * sizeof(float);
+    const size_t slot_bytes = ((size_t)2 * kSR * RWP) * sizeof(float);
     int NS = (int)((size_t)(224 * 1024 - kTHeader) / slot_bytes);
     NS = NS >= 16 ? 16 : (NS >= 8 ? 8 : 4);
     p.NS = NS;
