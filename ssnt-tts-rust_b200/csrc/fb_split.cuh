@@ -11,9 +11,10 @@
 //   recursion CTA d:  twelve prep warps (sub-partitions 1-3) load log_emit/log_shift rows in sweep order
 //                     straight from global memory, convert them (EX2, length masks) and write the
 //                     probabilities into the shared-memory ring; the recursion warp (alone on
-//                     sub-partition 0 but for three mostly sleeping copy-out warps) sweeps ALL T rows
-//                     without phases or barriers; the copy-out warps move its state rows to the global
-//                     scratch A_d (alpha(t) rows / beta(t+1) rows with their lane exponents).
+//                     sub-partition 0 but for three mostly sleeping publisher warps) sweeps ALL T rows
+//                     without phases or barriers and stores its state rows straight to the global scratch
+//                     A_d (alpha(t) rows / beta(t+1) rows, lane exponents in the first row of each stage);
+//                     the publisher warps fence at GPU scope and flag the rows to the gradient CTAs.
 //   gradient CTA:     sixteen identical warps; a frame's occupancies need alpha(t) and beta(t+1), i.e. a
 //                     fresh row of one sweep's second half and an old row of the other sweep's first
 //                     half; the probabilities are recomputed from the inputs (still in L2).  The
