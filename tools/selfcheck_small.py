@@ -1,4 +1,4 @@
-"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck); results are
+"""Small invocations of every kernel family (a quick self-check on a GPU box; compute-sanitizer is closed on this pool); results are
 compared with the oracle so that a silent corruption shows up too."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
