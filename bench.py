@@ -42,8 +42,10 @@ WORKLOADS = {
     "cfg1": (1, 120, 32),
     "cfg2": (32, 800, 128),
     "cfg5s": (512, 2000, 256),   # a 1/8 slice of configs[4] (B=4096) per GPU
+    "cfg3": (32, 800, 128),      # tone-latent lattice, K = 4 tone classes (BASELINE configs[2])
 }
-BYTES_PER_CELL = 16  # read log_emit+log_shift, write grad_emit+grad_shift (fp32)
+TONE_K = {"cfg3": 4}             # workloads that run the tone-latent lattice, and their class count
+BYTES_PER_CELL = 16  # read log_emit+log_shift, write grad_emit+grad_shift (fp32); x K for the tone lattice
 
 
 def load_product():
@@ -101,6 +103,24 @@ def synthetic_torch(b0, B, T, U, device, seed=1234):
     return le, ls
 
 
+def synthetic_tone_numpy(b0, B, T, U, K, seed=1234):
+    """Tone-latent inputs: the two-way emit/shift split per (cell, class) from the same counter hash
+    (the class axis is folded into the token axis), log_tone = log_softmax of N(0,1)^K."""
+    le, ls = synthetic_numpy(b0, B, T, U * K, seed)
+    z, _ = synthetic_numpy(b0, B, 1, U * K, seed + 1)
+    z = z.reshape(B, U, K).astype(np.float64)
+    lt = z - np.log(np.exp(z).sum(-1, keepdims=True))
+    return le.reshape(B, T, U, K), ls.reshape(B, T, U, K), lt.astype(np.float32)
+
+
+def synthetic_tone_torch(b0, B, T, U, K, device, seed=1234):
+    import torch
+    le, ls = synthetic_torch(b0, B, T, U * K, device, seed)
+    z, _ = synthetic_torch(b0, B, 1, U * K, device, seed + 1)
+    lt = torch.log_softmax(z.reshape(B, U, K).double(), dim=-1).float().contiguous()
+    return le.reshape(B, T, U, K), ls.reshape(B, T, U, K), lt
+
+
 # ---- clocks -------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -152,19 +172,24 @@ def measured_peak_gbs():
 
 
 # ---- CPU arm ----------------------------------------------------------------------------------------------
-def cpu_arm(B, T, U, budget_s=12.0, min_reps=2, max_reps=200):
+def cpu_arm(B, T, U, budget_s=12.0, min_reps=2, max_reps=200, K=0):
     """Times the oracle's fp32 port (multi-threaded over the batch like rayon) on one batch of
     the workload, repeated until ~budget_s of wall time.  Returns (cells/s, cores, reps, s/step)."""
     import oracle
     oracle.build()
     cores = oracle.get_threads()
-    le, ls = synthetic_numpy(0, B, T, U)
-    oracle.forward_backward(le[:1], ls[:1], precision="f32")  # touch
+    if K:
+        inputs = synthetic_tone_numpy(0, B, T, U, K)
+        run = lambda: oracle.tone_latent_forward_backward(*inputs, precision="f32")
+    else:
+        inputs = synthetic_numpy(0, B, T, U)
+        run = lambda: oracle.forward_backward(*inputs, precision="f32")
+    oracle.forward_backward(*(x[:1] for x in synthetic_numpy(0, 1, 8, 4)), precision="f32")  # touch
     reps, t0 = 0, time.perf_counter()
     times = []
     while reps < max_reps and (reps < min_reps or time.perf_counter() - t0 < budget_s):
         s = time.perf_counter()
-        oracle.forward_backward(le, ls, precision="f32")
+        run()
         times.append(time.perf_counter() - s)
         reps += 1
     per = float(np.median(times))
@@ -179,12 +204,18 @@ def run_reference(args):
     import oracle
     oracle.build()
     cores = oracle.get_threads()
-    le, ls = synthetic_numpy(0, B, T, U)
+    K = TONE_K.get(args.workload, 0)
+    if K:
+        inputs = synthetic_tone_numpy(0, B, T, U, K)
+        run = lambda: oracle.tone_latent_forward_backward(*inputs, precision="f32")
+    else:
+        inputs = synthetic_numpy(0, B, T, U)
+        run = lambda: oracle.forward_backward(*inputs, precision="f32")
     for _ in range(max(args.warmup, 1)):
-        oracle.forward_backward(le, ls, precision="f32")
+        run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.forward_backward(le, ls, precision="f32")
+        run()
     dt = time.perf_counter() - t0
     cells = B * T * U
     val = cells * args.steps / dt
@@ -192,7 +223,7 @@ def run_reference(args):
         "impl": "reference", "metric": "ssnt_fwd_bwd_lattice_cells_per_sec", "value": val, "unit": "cells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: SSNT loss+grad B={B} U={U} T={T} fp32 on host cores",
+        "config": {"workload": f"{args.workload}: {'tone-latent (K=%d) ' % K if K else ''}SSNT loss+grad B={B} U={U} T={T} fp32 on host cores",
                    "note": "reference crate has no forward-backward and cannot be built here (no cargo); "
                            "this arm is the oracle's fp32 C++ port of the authored spec, batch-parallel "
                            "over all host cores like rayon"},
@@ -223,26 +254,39 @@ def run_b200(args):
     P.lib()
     P.set_fb_kernel(args.fb_kernel)
     B, T, U = WORKLOADS[args.workload]
+    K = TONE_K.get(args.workload, 0)      # 0: the plain lattice
+    kk = K or 1
     cells = B * T * U
-    set_bytes = cells * 4 * 4 + P.forward_backward_workspace_bytes(B, T, U)
+    ws_bytes = (P.tone_latent_forward_backward_workspace_bytes(B, T, U, K) if K
+                else P.forward_backward_workspace_bytes(B, T, U))
+    set_bytes = cells * kk * 4 * 4 + ws_bytes
     nsets = max(2, min(16, int(np.ceil(3.2 * 126e6 / set_bytes))))
     if set_bytes * nsets > 60e9:
         nsets = max(1, int(60e9 // set_bytes))
     b_global0 = rank * B
     sets = []
     for s in range(nsets):
-        le, ls = synthetic_torch(b_global0 + s * world * B, B, T, U, dev)
-        ws = torch.empty(P.forward_backward_workspace_bytes(B, T, U), dtype=torch.uint8, device=dev)
-        out = (torch.empty(B, device=dev), torch.empty(1, device=dev),
-               torch.empty(B, T, U, device=dev), torch.empty(B, T, U, device=dev))
-        sets.append((le, ls, ws, out))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if K:
+            inp = synthetic_tone_torch(b_global0 + s * world * B, B, T, U, K, dev)
+            out = (torch.empty(B, device=dev), torch.empty(1, device=dev), torch.empty(B, T, U, K, device=dev),
+                   torch.empty(B, T, U, K, device=dev), torch.empty(B, U, K, device=dev))
+        else:
+            inp = synthetic_torch(b_global0 + s * world * B, B, T, U, dev)
+            out = (torch.empty(B, device=dev), torch.empty(1, device=dev),
+                   torch.empty(B, T, U, device=dev), torch.empty(B, T, U, device=dev))
+        sets.append((inp, ws, out))
     torch.cuda.synchronize()
+    product_call = P.tone_latent_forward_backward if K else P.forward_backward
+
+    def run_set(i):
+        inp, ws, out = sets[i % nsets]
+        return product_call(*inp, workspace=ws, out=out)
 
     pending = []
 
     def step(i):
-        le, ls, ws, out = sets[i % nsets]
-        ll, loss, ge, gs = P.forward_backward(le, ls, workspace=ws, out=out)
+        loss = run_set(i)[1]
         if world > 1:
             # the path's only collective: 4 bytes.  Issued asynchronously (NCCL's stream waits for this
             # step's kernel; the next step's kernel does not wait for the all-reduce), completed by
@@ -281,8 +325,7 @@ def run_b200(args):
             t_end = time.perf_counter() + 0.4
             i = 0
             while time.perf_counter() < t_end:
-                le, ls, ws, out = sets[i % nsets]
-                P.forward_backward(le, ls, workspace=ws, out=out)
+                run_set(i)
                 i += 1
             torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -297,8 +340,7 @@ def run_b200(args):
     ksteps = max(args.steps, 10)
     kev0.record()
     for i in range(ksteps):
-        le, ls, ws, out = sets[i % nsets]
-        P.forward_backward(le, ls, workspace=ws, out=out)
+        run_set(i)
     kev1.record()
     torch.cuda.synchronize()
     k_ms = kev0.elapsed_time(kev1) / ksteps
@@ -307,16 +349,14 @@ def run_b200(args):
     # ---- e2e through the C-ABI with HOST (pinned) buffers --------------------------------------
     hsets = []
     for s in range(2):
-        le, ls, _, _ = sets[s % nsets]
-        h = dict(le=le.cpu().pin_memory(), ls=ls.cpu().pin_memory(),
-                 ll=torch.empty(B).pin_memory(), loss=torch.empty(1).pin_memory(),
-                 ge=torch.empty(B, T, U).pin_memory(), gs=torch.empty(B, T, U).pin_memory())
+        inp, _, out = sets[s % nsets]
+        h = dict(inp=[x.cpu().pin_memory() for x in inp], out=[torch.empty(x.shape).pin_memory() for x in out])
+        h["loss"] = h["out"][1]
         hsets.append(h)
 
     def e2e_step(i):
         h = hsets[i % 2]
-        P.forward_backward(h["le"].numpy(), h["ls"].numpy(),
-                           out=(h["ll"].numpy(), h["loss"].numpy(), h["ge"].numpy(), h["gs"].numpy()))
+        product_call(*(x.numpy() for x in h["inp"]), out=tuple(x.numpy() for x in h["out"]))
         if world > 1:
             l = h["loss"].to(dev)
             dist.all_reduce(l)
@@ -338,11 +378,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    h2d = 2 * cells * 4
-    d2h = 2 * cells * 4 + B * 4 + 4
+    h2d = sum(x.numel() * 4 for x in hsets[0]["inp"])
+    d2h = sum(x.numel() * 4 for x in hsets[0]["out"])
 
     peak, peak_src = measured_peak_gbs()
-    achieved = BYTES_PER_CELL * cells / (k_ms * 1e-3) / 1e9
+    achieved = BYTES_PER_CELL * kk * cells / (k_ms * 1e-3) / 1e9
     line = {
         "metric": "ssnt_fwd_bwd_lattice_cells_per_sec",
         "value": world * cells * args.steps / (ms * 1e-3),
@@ -352,24 +392,30 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: batched SSNT loss+grad fp32 B={B} U={U} T={T} per GPU "
-                        f"(BASELINE configs[1] when cfg2), full lengths",
+            "workload": (f"{args.workload}: tone-latent (K={K}) SSNT loss+grad fp32 B={B} U={U} T={T} per GPU "
+                         f"(BASELINE configs[2]), full lengths" if K else
+                         f"{args.workload}: batched SSNT loss+grad fp32 B={B} U={U} T={T} per GPU "
+                         f"(BASELINE configs[1] when cfg2), full lengths"),
             "global_batch": world * B, "parallelism": f"batch-sharded dp{world}, all-reduce of the scalar loss only",
             "l2_policy": f"rotating {nsets} independent input/output/scratch sets "
                          f"({nsets * set_bytes / 1e6:.0f} MB > 3x 126 MB L2); inputs come from HBM every step",
             "fb_kernel": {4: "fb_split_kernel (block-float; cluster of 4 CTAs per utterance: 2 recursion CTAs + 2 helper CTAs, TMA ring, DSMEM flags)",
                           2: "fb_bf_kernel (block-float, warp-specialised cluster of 2 CTAs, TMA ring)",
                           1: "fb_log_warp_kernel (log domain, cluster of 2 warps, TMA ring)",
-                          0: "fb_generic_kernel"}.get(kernel_kind),
+                          0: "fb_generic_kernel"}.get(kernel_kind) if not K else
+                         "tone_split_kernel (block-float; cluster of 4 CTAs per utterance) + tone_fb_kernel "
+                         "(log domain, only the utterances the first kernel flagged)",
             "loss_check": final_loss,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells},
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * kk * cells},
         "e2e": {"value": world * cells * e2e_steps / e2e_s, "unit": "cells/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "loss_check": e2e_loss},
-        "gpu_launches": args.steps,  # one fb kernel launch per step (the all-reduce is NCCL's)
+        # one fb kernel launch per step (tone lattice: block-float kernel + masked log-domain kernel); the
+        # all-reduce is NCCL's
+        "gpu_launches": args.steps * (2 if K else 1),
         "clocks": clk.summary(),
     }
     traffic_file = os.path.join(ROOT, "profiles", "fb_traffic_bytes.json")
@@ -379,9 +425,9 @@ def run_b200(args):
         except Exception:
             pass
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, reps, per = cpu_arm(B, T, U)
+        v, cores, reps, per = cpu_arm(B, T, U, K=K)
         line["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
-                                "sample": f"{reps} passes over one B={B} U={U} T={T} batch, "
+                                "sample": f"{reps} passes over one B={B} U={U} T={T}{' K=%d' % K if K else ''} batch, "
                                           f"{per * 1e3:.1f} ms each (oracle fp32 port, batch-parallel)"}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -215,8 +215,9 @@ def ssnt_tts_v2_beam_search_decode(h, log_prob_history, is_finished, total_durat
     next_u, next_is_finished, next_total_duration, beam_branch — each [B, W]."""
     c = _Call(h)
     B, W = int(h.shape[0]), int(beam_width)
-    if test_mode:
-        output_length = np.zeros(B, np.int32)
+    if test_mode:  # in the caller's memory space: no host-to-device copy inside a device-pointer step
+        output_length = (_torch().zeros(B, dtype=_torch().int32, device=c.dev) if c.device
+                         else np.zeros(B, np.int32))
     args = [c.inp(h, "f32"), c.inp(log_prob_history, "f32"), c.inp(is_finished, "bool"),
             c.inp(total_duration, "i32"), c.inp(duration_table, "i32"), c.inp(t, "i32"), c.inp(u, "i32"),
             c.inp(input_length, "i32"), c.inp(output_length, "i32")]
@@ -318,20 +319,33 @@ def forward_backward(log_emit, log_shift, t_len=None, u_len=None, workspace=None
     return ll, loss, ge, gs
 
 
-def tone_latent_forward_backward(log_emit, log_shift, log_tone, t_len=None, u_len=None):
+def tone_latent_forward_backward_workspace_bytes(batch_size, max_t, max_u, tone_class_size) -> int:
+    return int(lib().tone_latent_forward_backward_workspace_bytes(batch_size, max_t, max_u, tone_class_size))
+
+
+def tone_latent_forward_backward(log_emit, log_shift, log_tone, t_len=None, u_len=None, workspace=None, out=None):
     """Tone-latent marginalised lattice.  log_emit, log_shift: [B, T, U, K]; log_tone: [B, U, K].
-    Returns (log_likelihood[B], loss[1], grad_emit, grad_shift, grad_tone)."""
+    Returns (log_likelihood[B], loss[1], grad_emit, grad_shift, grad_tone).  ``workspace`` and ``out``
+    as in forward_backward."""
     c = _Call(log_emit)
     B, T, U, K = (int(s) for s in log_emit.shape)
     a = [c.inp(log_emit, "f32"), c.inp(log_shift, "f32"), c.inp(log_tone, "f32"), c.inp(t_len, "i32"),
          c.inp(u_len, "i32")]
-    ll, p_ll = c.out((B,), "f32")
-    loss, p_loss = c.out((1,), "f32")
-    ge, p_ge = c.out((B, T, U, K), "f32")
-    gs, p_gs = c.out((B, T, U, K), "f32")
-    gt, p_gt = c.out((B, U, K), "f32")
+    if out is not None:
+        ll, loss, ge, gs, gt = out
+        ptr = (lambda x: c_void_p(x.data_ptr())) if c.device else (lambda x: c_void_p(x.ctypes.data))
+        p_ll, p_loss, p_ge, p_gs, p_gt = ptr(ll), ptr(loss), ptr(ge), ptr(gs), ptr(gt)
+    else:
+        ll, p_ll = c.out((B,), "f32")
+        loss, p_loss = c.out((1,), "f32")
+        ge, p_ge = c.out((B, T, U, K), "f32")
+        gs, p_gs = c.out((B, T, U, K), "f32")
+        gt, p_gt = c.out((B, U, K), "f32")
+    ws_ptr, ws_bytes = c_void_p(0), 0
+    if workspace is not None:
+        ws_ptr, ws_bytes = c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
     lib().tone_latent_forward_backward(*a, c_int(B), c_int(T), c_int(U), c_int(K), p_ll, p_loss, p_ge, p_gs,
-                                       p_gt, c_void_p(0), c_size_t(0))
+                                       p_gt, ws_ptr, c_size_t(ws_bytes))
     return ll, loss, ge, gs, gt
 
 
