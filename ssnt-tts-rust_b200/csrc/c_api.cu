@@ -343,20 +343,63 @@ void tone_latent_forward_backward(const float* log_emit, const float* log_shift,
         launch_tone_forward_backward(a, current_stream());
         return;
     }
-    HostCall c;
-    const size_t cells = n3(batch_size, max_t, max_u) * (size_t)(tone_class_size > 0 ? tone_class_size : 0);
-    const size_t tcells = n3(batch_size, max_u, tone_class_size);
-    const size_t B = (size_t)(batch_size > 0 ? batch_size : 0);
-    auto dle = c.in(log_emit, cells); auto dls = c.in(log_shift, cells); auto dlt = c.in(log_tone, tcells);
-    const int* dtl = t_len ? c.in(t_len, B) : nullptr;
-    const int* dul = u_len ? c.in(u_len, B) : nullptr;
-    float dummy_loss = 0.0f;
-    auto oll = c.out(log_likelihood, B); auto olo = c.out(loss ? loss : &dummy_loss, 1);
-    auto oge = c.out(grad_emit, cells); auto ogs = c.out(grad_shift, cells); auto ogt = c.out(grad_tone, tcells);
-    ToneFbArgs a{dle, dls, dlt, dtl, dul, batch_size, max_t, max_u, tone_class_size, oll, olo, oge, ogs, ogt,
-                 nullptr, 0};
-    launch_tone_forward_backward(a, c.stream());
-    c.finish();
+    // Host buffers: the same chunked H2D / kernel / D2H pipeline as ssnt_tts_forward_backward above.
+    const int K = tone_class_size > 0 ? tone_class_size : 0;
+    const int B = batch_size > 0 ? batch_size : 0;
+    const size_t slab = n2(max_t, max_u) * (size_t)K, tslab = n2(max_u, K);
+    float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
+    float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
+    float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
+    float* d_gs = (float*)device_scratch(7, B * slab * sizeof(float) + 16);
+    float* d_ll = (float*)device_scratch(8, (size_t)B * sizeof(float) + 16);
+    int* d_tl = (int*)device_scratch(9, (size_t)B * sizeof(int) + 16);
+    int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
+    float* d_lt = (float*)device_scratch(11, B * tslab * sizeof(float) + 16);
+    float* d_gt = (float*)device_scratch(12, B * tslab * sizeof(float) + 16);
+    int nchunks = 1;
+    // measured on config 3 (2 x 105 MB): 2 chunks 3.26 ms, 4: 3.06, 6: 2.81, 8: 3.02 (unchunked 4.04)
+    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 12 ? 6 : (B >= 8 ? 4 : 2);
+    if (const char* e = std::getenv("SSNT_FB_CHUNKS")) {  // tuning aid
+        nchunks = std::atoi(e);
+        nchunks = nchunks < 1 ? 1 : (nchunks > kMaxChunks ? kMaxChunks : nchunks);
+        if (nchunks > B) nchunks = B > 0 ? B : 1;
+    }
+    const int per = (B + nchunks - 1) / nchunks;
+    // every chunk's workspace starts 256-byte aligned (the block-float kernel needs 16)
+    const size_t ws_each = (tone_fb_workspace_bytes(per, max_t, max_u, K) + 255) & ~(size_t)255;
+    char* ws = (char*)device_scratch(1, ws_each * nchunks);
+    tls_aux.init();
+    cudaStream_t main_stream = current_stream();
+    SSNT_CUDA(cudaEventRecord(tls_aux.start, main_stream));
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
+        if (nb <= 0) break;
+        cudaStream_t s = tls_aux.k[c % kComputeStreams];
+        SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
+        const size_t o = (size_t)b0 * slab, nbytes = (size_t)nb * slab * sizeof(float);
+        const size_t ot = (size_t)b0 * tslab, tbytes = (size_t)nb * tslab * sizeof(float);
+        SSNT_CUDA(cudaMemcpyAsync(d_lt + ot, log_tone + ot, tbytes, cudaMemcpyHostToDevice, s));
+        SSNT_CUDA(cudaMemcpyAsync(d_le + o, log_emit + o, nbytes, cudaMemcpyHostToDevice, s));
+        SSNT_CUDA(cudaMemcpyAsync(d_ls + o, log_shift + o, nbytes, cudaMemcpyHostToDevice, s));
+        if (t_len) SSNT_CUDA(cudaMemcpyAsync(d_tl + b0, t_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (u_len) SSNT_CUDA(cudaMemcpyAsync(d_ul + b0, u_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
+        ToneFbArgs a{d_le + o, d_ls + o, d_lt + ot, t_len ? d_tl + b0 : nullptr, u_len ? d_ul + b0 : nullptr, nb,
+                     max_t, max_u, tone_class_size, d_ll + b0, nullptr, d_ge + o, d_gs + o, d_gt + ot,
+                     ws + (size_t)c * ws_each, ws_each};
+        launch_tone_forward_backward(a, s);
+        SSNT_CUDA(cudaMemcpyAsync(grad_emit + o, d_ge + o, nbytes, cudaMemcpyDeviceToHost, s));
+        SSNT_CUDA(cudaMemcpyAsync(grad_shift + o, d_gs + o, nbytes, cudaMemcpyDeviceToHost, s));
+        SSNT_CUDA(cudaMemcpyAsync(grad_tone + ot, d_gt + ot, tbytes, cudaMemcpyDeviceToHost, s));
+        used = c + 1;
+    }
+    for (int i = 0; i < kComputeStreams && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.k[i]));
+    if (B > 0) SSNT_CUDA(cudaMemcpy(log_likelihood, d_ll, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost));
+    if (loss) {
+        double acc = 0.0;  // loss = -sum_b ll[b] in batch order, in double (as the kernel's own reduction)
+        for (int b2 = 0; b2 < B; ++b2) acc -= (double)log_likelihood[b2];
+        *loss = (float)acc;
+    }
 }
 
 // ---- runtime side channel ----------------------------------------------------------------------

@@ -255,6 +255,25 @@ def test_tone_latent_config3_B32_U128_T800_K4(product, oracle_mod):
     np.testing.assert_allclose(gt.sum(axis=2), 1.0, atol=3e-4)
 
 
+@pytest.mark.parametrize("B", [9, 10, 13])
+def test_tone_latent_host_buffers_chunked(product, oracle_mod, B):
+    """Host-pointer call large enough for the chunked H2D / kernel / D2H pipeline (c_api.cu), with a
+    ragged last chunk (B=10 -> 3,3,3,1; B=13 -> six chunks 3,3,3,3,1) and ragged lengths; loss = -sum of the finite likelihoods' total."""
+    T, U, K = 300, 64, 4
+    le, ls, lt = make_inputs(B, T, U, seed=B, K=K)
+    t_len, u_len = ragged_lengths(B, T, U, seed=B + 1)
+    t_len[0], u_len[0] = T, U
+    want = oracle_mod.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    got = product.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
+    _check_tone(got, want)
+    got2 = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
+    for i, (a, b) in enumerate(zip(got, got2)):  # per-utterance results do not depend on the chunking
+        if i == 1:
+            np.testing.assert_allclose(_np(a), _np(b), rtol=1e-6)
+        else:
+            np.testing.assert_array_equal(_np(a), _np(b))
+
+
 def test_tone_latent_infeasible(product, oracle_mod):
     le, ls, lt = make_inputs(3, 6, 8, seed=9, K=2)
     t_len, u_len = np.array([6, 0, 4], np.int32), np.array([7, 3, 4], np.int32)
