@@ -261,19 +261,22 @@ def run_b200(args):
                 else P.forward_backward_workspace_bytes(B, T, U))
     set_bytes = cells * kk * 4 * 4 + ws_bytes
     nsets = max(2, min(16, int(np.ceil(3.2 * 126e6 / set_bytes))))
+    if world > 1:
+        nsets = max(nsets, 16)   # four graphs of four steps: slack between a step's all-reduce and its buffers' reuse
     if set_bytes * nsets > 60e9:
         nsets = max(1, int(60e9 // set_bytes))
     b_global0 = rank * B
     sets = []
+    loss_all = torch.zeros(nsets, device=dev)   # the sets' scalar losses, contiguous (one all-reduce can carry several)
     for s in range(nsets):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if K:
             inp = synthetic_tone_torch(b_global0 + s * world * B, B, T, U, K, dev)
-            out = (torch.empty(B, device=dev), torch.empty(1, device=dev), torch.empty(B, T, U, K, device=dev),
+            out = (torch.empty(B, device=dev), loss_all[s:s + 1], torch.empty(B, T, U, K, device=dev),
                    torch.empty(B, T, U, K, device=dev), torch.empty(B, U, K, device=dev))
         else:
             inp = synthetic_torch(b_global0 + s * world * B, B, T, U, dev)
-            out = (torch.empty(B, device=dev), torch.empty(1, device=dev),
+            out = (torch.empty(B, device=dev), loss_all[s:s + 1],
                    torch.empty(B, T, U, device=dev), torch.empty(B, T, U, device=dev))
         sets.append((inp, ws, out))
     torch.cuda.synchronize()
@@ -309,14 +312,15 @@ def run_b200(args):
     # stream) and the timed region replays them: no Python between the launches.  N > 1 adds a 4-byte
     # all-reduce per step, and issuing kernel + all-reduce from Python costs more host time than the
     # kernel runs (54-62 us per step measured at N=2).  NCCL work is kept OUT of the graphs (capturing
-    # it hung here): the sets are split over two graphs, and after replaying one the host issues its
-    # steps' all-reduces asynchronously while the other graph's kernels run; a graph is replayed again
+    # it hung here): the sets are split over a few graphs, and after replaying one the host issues ONE
+    # asynchronous all-reduce carrying its steps' scalar losses (4 bytes per step; issuing them one by one
+    # left the run host-bound at N=4: 54 us per step) while the other graphs' kernels run; a graph is replayed again
     # only after its previous all-reduces have read its loss buffers (a stream-level wait).  Steps left
     # over when K is not a multiple of the graph length run eagerly.
     graphs = []
     if not args.no_graph:
-        groups = ([list(range(0, nsets // 2)), list(range(nsets // 2, nsets))] if world > 1 and nsets >= 2
-                  else [list(range(nsets))])
+        ngroups = (4 if nsets >= 8 else 2) if world > 1 and nsets >= 2 else 1
+        groups = [list(range(j * nsets // ngroups, (j + 1) * nsets // ngroups)) for j in range(ngroups)]
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -338,9 +342,8 @@ def run_b200(args):
                 w.wait()
             works.clear()
             g.replay()
-            if world > 1:
-                for i in idxs:
-                    works.append(dist.all_reduce(sets[i][2][1], async_op=True))
+            if world > 1:  # this replay's scalar losses (one per step, contiguous) in one collective
+                works.append(dist.all_reduce(loss_all[idxs[0]:idxs[-1] + 1], async_op=True))
             done += len(idxs)
             loss = sets[idxs[-1]][2][1]
             gi = (gi + 1) % len(graphs)
@@ -455,7 +458,8 @@ def run_b200(args):
                          f"(BASELINE configs[1] when cfg2), full lengths"),
             "global_batch": world * B, "parallelism": f"batch-sharded dp{world}, all-reduce of the scalar loss only",
             "launch": (f"{len(graphs)} CUDA graph(s) of {len(graphs[0][1])} steps each (one C-ABI call per step, captured), "
-                       "replayed" + ("; the loss all-reduces are issued by the host after each replay" if world > 1 else "")
+                       "replayed" + ("; after each replay the host issues one NCCL all-reduce carrying that replay's scalar losses "
+                                     "(4 bytes per step), completed inside the timed region" if world > 1 else "")
                        if graphs else "one C-ABI call per step from the host"),
             "l2_policy": f"rotating {nsets} independent input/output/scratch sets "
                          f"({nsets * set_bytes / 1e6:.0f} MB > 3x 126 MB L2); inputs come from HBM every step",
