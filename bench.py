@@ -249,6 +249,11 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The 4-byte all-reduce must not take SMs from the lattice kernel: at B=32 its 32 clusters of 4 CTAs
+        # need four clusters in every GPC (8 GPCs x 18-20 SMs), and a multi-channel NCCL kernel that occupies
+        # a few SMs makes the last cluster wait for a whole kernel (step time doubles).  One channel = one CTA.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")
         dist.init_process_group("nccl", device_id=dev)
     P = load_product()
     P.lib()
@@ -365,6 +370,7 @@ def run_b200(args):
         drain()
         ev1.record()
         torch.cuda.synchronize()
+        final_loss = float(loss.item())   # the last timed step's (all-reduced) loss, before anything overwrites it
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -383,7 +389,6 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
-    final_loss = float(loss.item())
 
     # kernel-only timing for the roofline (no collective, same rotation)
     kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
