@@ -267,7 +267,7 @@ def run_b200(args):
     set_bytes = cells * kk * 4 * 4 + ws_bytes
     nsets = max(2, min(16, int(np.ceil(3.2 * 126e6 / set_bytes))))
     if world > 1:
-        nsets = max(nsets, 16)   # four graphs of four steps: slack between a step's all-reduce and its buffers' reuse
+        nsets = max(nsets, 32)   # four graphs of eight steps: slack between a step's all-reduce and its buffers' reuse
     if set_bytes * nsets > 60e9:
         nsets = max(1, int(60e9 // set_bytes))
     b_global0 = rank * B
