@@ -393,3 +393,31 @@ def test_tone_latent_block_float_does_not_fall_back_on_typical_inputs(product):
     product.tone_latent_forward_backward(le, ls, lt)
     torch.cuda.synchronize()
     assert product.fb_fallback_count() == before
+
+
+def test_device_pointer_call_is_capturable_in_a_cuda_graph(product, oracle_mod):
+    """bench.py replays the step's C-ABI call from CUDA graphs: a device-pointer call with a caller-owned
+    workspace enqueues its launch on the stream set through ssnt_tts_set_stream and does nothing a capture
+    forbids (no allocation, no synchronisation); replays give the eager call's results bit for bit."""
+    import torch
+    B, T, U = 6, 200, 128
+    le, ls = make_inputs(B, T, U, seed=77)
+    want = oracle_mod.forward_backward(le, ls)
+    dle, dls = _dev(le), _dev(ls)
+    ws = torch.empty(product.forward_backward_workspace_bytes(B, T, U), dtype=torch.uint8, device="cuda")
+    out = (torch.empty(B, device="cuda"), torch.empty(1, device="cuda"),
+           torch.empty(B, T, U, device="cuda"), torch.empty(B, T, U, device="cuda"))
+    product.forward_backward(dle, dls, workspace=ws, out=out)
+    torch.cuda.synchronize()
+    eager = [o.clone() for o in out]
+    for o in out:
+        o.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        product.forward_backward(dle, dls, workspace=ws, out=out)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, out):
+        assert torch.equal(a, b)
+    _check(out, want)
