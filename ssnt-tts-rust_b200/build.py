@@ -14,12 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssnt_tts_c.so")
 SOURCES = ["runtime.cu", "fb_kernels.cu", "tone_fb_kernels.cu", "tone_bf.cu", "beam_kernels.cu", "trace_kernels.cu",
-           "edit_distance.cu", "decode_loop.cu", "c_api.cu"]
+           "edit_distance.cu", "c_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-fmad=true",
-] + (["-DSSNT_BF_DEBUG_VARIANTS"] if os.environ.get("SSNT_BF_DEBUG_VARIANTS") else [])
+] + (["-DSSNT_BF_DEBUG_VARIANTS"] if os.environ.get("SSNT_BF_DEBUG_VARIANTS") else []) \
+  + (["-DSSNT_TP_TRACE"] if os.environ.get("SSNT_TP_TRACE") else [])
 
 
 def _nvcc() -> str:

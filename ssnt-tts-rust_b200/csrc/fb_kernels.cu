@@ -14,6 +14,7 @@
 //            bases): one CTA per utterance, one thread per token, rows in shared memory, log2
 //            domain with one integer offset per token.
 #include "fb_split.cuh"
+#include "fb_tp.cuh"
 
 namespace ssnt {
 namespace {
@@ -36,7 +37,9 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
     int U = a.u_len ? a.u_len[b] : a.max_u;
     T = min(max(T, 0), a.max_t);
     U = min(max(U, 0), a.max_u);
-    if (T <= 0 || U <= 0 || U > T) {
+    if (p.only && p.only[b] == 0u) {
+        // re-run mode: this utterance's block-float results stand
+    } else if (T <= 0 || U <= 0 || U > T) {
         // No monotonic path: ll = -inf, every gradient 0.  Uniform for both CTAs of the cluster.
         const size_t slab = (size_t)a.max_t * a.max_u;
         float* g = (rank == 0 ? a.grad_emit : a.grad_shift) + (size_t)b * slab;
@@ -44,6 +47,7 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
         for (int t = 0; t < a.max_t; ++t) store_cells_cs<CPL>(g + (size_t)t * a.max_u, lane * CPL, a.max_u, zeros);
         if (rank == 0 && lane == 0) a.log_likelihood[b] = -INFINITY;
     } else {
+        if (p.only && rank == 0 && lane == 0) atomicAdd(p.fallbacks, 1u);
         log_lattice_cta<CPL>(p, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw),
                              reinterpret_cast<float*>(smem_raw + 128), cluster);
     }
@@ -362,7 +366,53 @@ void launch_split(const SplitParams& p, size_t smem, cudaStream_t stream) {
 
 inline int round_up4(int x) { return (x + 3) & ~3; }
 
+// Time-parallel path (kind 6): chunk operators, boundary vectors, chunk interiors; one warp per CTA throughout.
+template <int CPL>
+void launch_tp(const TpParams& p, cudaStream_t stream) {
+    constexpr int L = kTpL;
+    const FbArgs& a = p.a;
+    const size_t chunk_smem = 128 + (size_t)2 * L * a.max_u * sizeof(float);
+    constexpr int NT = 32 * CPL;
+    constexpr int NS = NT <= 128 ? 16 : 8;   // 139 KB of operators in flight per (utterance, direction)
+    const size_t ring_smem = 256 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (ring_smem > configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        configured = ring_smem;
+    }
+    const unsigned tasks = (unsigned)a.batch_size * (unsigned)p.C;
+    static const int stages = [] { const char* e = std::getenv("SSNT_TP_DEBUG_STAGES"); return e ? std::atoi(e) : 3; }();
+    if (stages >= 1) tp_build_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+    if (stages >= 2) tp_combine_kernel<NT, L, NS><<<(unsigned)a.batch_size * 2u, NT + 32, ring_smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+    if (stages >= 3) tp_fill_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+}
+
 }  // namespace
+
+// Time-parallel path (kind 6): region 0 holds the chunk operators Q [B][C][L+1][UP] and is re-used as the scratch
+// rows of the log-domain re-run; then the boundary vectors A, Bv [B][C+1][UP+32], the two likelihood estimates and
+// the status words.
+struct TpLayout {
+    int CPL, UP, C, SU;
+    size_t region0, vec, total;
+};
+static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
+    if (max_u % 4 != 0 || max_u > 256 || max_u <= 0 || max_t <= 0 || B <= 0) return false;
+    l.CPL = max_u <= 64 ? 2 : (max_u <= 128 ? 4 : 8);
+    l.UP = 32 * l.CPL;
+    l.C = (max_t + kTpL - 1) / kTpL;
+    l.SU = max_u + 32;
+    const size_t q = (size_t)B * l.C * (kTpL + 1) * l.UP * sizeof(float);
+    const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
+    l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
+    l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
+    l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
+              (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
+    return true;
+}
 
 // Split kernel (kind 4): state rows A [B][2][nstp*8][SU] (both sweeps, sweep order) and status [B].
 static size_t split_workspace_bytes(int B, int max_t, int max_u) {
@@ -383,6 +433,8 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     size_t n = warp_bytes > gen_bytes ? warp_bytes : gen_bytes;
     const size_t split_bytes = split_workspace_bytes(B, max_t, max_u);
     n = n > split_bytes ? n : split_bytes;
+    TpLayout tl;
+    if (tp_layout(B, max_t, max_u, tl)) n = n > tl.total ? n : tl.total;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -424,6 +476,47 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
     // few utterances (one wave of 4-CTA clusters): the split-role kernel keeps the recursion SMs free of
     // everything else; many utterances: the fused kernel needs half the SMs per utterance
     if (kind < 0) kind = (split_ok && a.batch_size * 4 <= sm_count() - 16) ? 4 : bf_ok ? 2 : (warp_ok ? 1 : 0);
+    if (kind == 6 || kind == 7) {
+        TpLayout tl;
+        SSNT_ASSERT(bf_ok && tp_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: time-parallel kernels forced on an unsupported shape");
+        tls_last_kind = kind;
+        TpParams p;
+        p.a = a;
+        char* base = (char*)ws;
+        p.Q = (float*)base;
+        p.A = (float*)(base + tl.region0);
+        p.Bv = (float*)(base + tl.region0 + tl.vec);
+        p.zlg = (float*)(base + tl.region0 + 2 * tl.vec);
+        p.status = (unsigned*)(base + tl.region0 + 2 * tl.vec + (((size_t)a.batch_size * 4 * sizeof(float) + 255) & ~(size_t)255));
+        p.C = tl.C;
+        p.UP = tl.UP;
+        const size_t stage = (size_t)(kTpL + 1) * tl.UP * sizeof(float);
+        int NS = (int)((size_t)(200 * 1024) / stage);
+        p.NS = NS > 16 ? 16 : NS;
+        p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
+        if (tl.CPL == 2) launch_tp<2>(p, stream);
+        else if (tl.CPL == 4) launch_tp<4>(p, stream);
+        else launch_tp<8>(p, stream);
+        // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
+        static const bool skip_log = [] { const char* e = std::getenv("SSNT_TP_DEBUG_STAGES"); return e && std::atoi(e) < 4; }();
+        if (skip_log) return;
+        LogParams lp;
+        lp.a = a;
+        lp.scratch = (float*)ws;
+        lp.SU = tl.SU;
+        lp.counter = counter;
+        lp.only = p.status;
+        lp.fallbacks = device_fallback_counter();
+        const size_t stage_bytes = (size_t)kG * (2 * a.max_u + lp.SU) * sizeof(float);
+        const bool latency_mode = (size_t)a.batch_size * 2 <= (size_t)sm_count();
+        int LNS = (int)((latency_mode ? 192 * 1024 : 52 * 1024) / stage_bytes);
+        lp.NS = LNS < 2 ? 2 : (LNS > 8 ? 8 : LNS);
+        const size_t smem = 128 + (size_t)lp.NS * stage_bytes;
+        if (tl.CPL == 2) launch_warp<2>(lp, smem, stream);
+        else if (tl.CPL == 4) launch_warp<4>(lp, smem, stream);
+        else launch_warp<8>(lp, smem, stream);
+        return;
+    }
     if (kind >= 4) SSNT_ASSERT(split_ok, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");

@@ -30,6 +30,9 @@ struct LogParams {
     int SU;          // scratch row stride in floats = round_up4(max_u) + 32 (32 lane offsets)
     int NS;          // pipeline stages
     unsigned* counter;
+    const unsigned* only = nullptr;  // optional [B]: run only the utterances whose word is non-zero (re-run of what a
+                                     // block-float kernel flagged); the others keep their results
+    unsigned* fallbacks = nullptr;   // counts the utterances re-run through `only`
 };
 
 // Returns through global memory: ll[b], gradients of rows [0, T), zeros for rows [T, max_t).

@@ -1,0 +1,508 @@
+// Time-parallel lattice forward-backward (kernel kind 6): the T-serial recursion is cut into chunks
+// of L frames whose transfer operators are built concurrently.
+//
+// The probability-domain recursion is linear:  alpha(t+1) = M_t alpha(t)  with the bidiagonal
+//   (M_t x)(u) = e(t,u) x(u) + s(t,u-1) x(u-1),      e = exp(log_emit), s = exp(log_shift),
+// and beta(t) = M_t^T beta(t+1) (SURVEY.md §8 a-FB; Emit/Shift semantics of src/lib.rs:187-225).
+// For chunk c = frames [cL, cL+L) the product  P_c = M_{cL+L-1} ... M_{cL}  is lower-banded with
+// bandwidth L+1, so it is held as L+1 diagonals  Q_c(i, d) = P_c(i, i-d).  Three kernels:
+//
+//   tp_build_kernel    one warp per (utterance, chunk): TMA-loads the chunk's 2·L rows, converts them
+//                      (EX2, length masks) and runs the L-row recursion on all L+1 diagonals at once
+//                      (registers; one shuffle per diagonal and row); writes Q_c.  Every chunk of
+//                      every utterance is independent: B·T/L warps, one wave.
+//   tp_combine_kernel  one warp per (utterance, direction): alpha_{c+1} = P_c alpha_c forward and
+//                      beta_c = P_c^T beta_{c+1} backward — the SAME operator serves both sweeps —
+//                      T/L banded mat-vecs instead of T dependent rows; operators stream through a TMA
+//                      ring.  Boundary vectors carry one power-of-two exponent per lane (block float).
+//   tp_fill_kernel     one warp per (utterance, chunk): from alpha_c and beta_{c+1} re-runs the L
+//                      rows of its chunk (alpha forward into registers, beta backward with the
+//                      gradients fused) and writes grad_emit / grad_shift with streaming stores.
+//
+// Critical path: ~2L rows + T/L mat-vecs instead of 2T rows.  Range: operators are plain fp32
+// products of L probabilities; boundary vectors are block-float.  Every frame's occupancies must sum
+// to 1 and the two sweeps' likelihoods must agree, else the utterance is flagged (status word) and
+// re-run by the log-domain kernel (fb_log_warp.cuh), like the other block-float kernels do.
+#pragma once
+#include "fb_log_warp.cuh"
+
+namespace ssnt {
+namespace lattice {
+
+constexpr int kTpL = 16;               // frames per chunk
+constexpr float kTpRowTol = 2e-5f;     // |sum_u occupancy(t,u) - 1| beyond this flags the utterance
+constexpr float kTpZTol = 3e-5f;       // |log2 Z_forward - log2 Z_backward| beyond this flags it
+
+enum TpStatus : unsigned { kTpBadZ = 1u, kTpBadRow = 2u, kTpForced = 4u };
+
+struct TpParams {
+    FbArgs a;
+    float* Q;          // [B][C][L+1][UP]   chunk operators, diagonal-major
+    float* A;          // [B][C+1][UP+32]   alpha at chunk boundaries: UP mantissas + 32 lane exponents (int)
+    float* Bv;         // [B][C+1][UP+32]   beta at chunk boundaries
+    float* zlg;        // [B][2][2]         (log2 mantissa, exponent as float) of Z from the forward / backward sweep
+    unsigned* status;  // [B]
+    int C;             // chunks per utterance = ceil(max_t / L)
+    int UP;            // padded token count = 32 * CPL
+    int NS;            // combine ring stages
+    int force_fallback;
+};
+
+// mbarrier wait by all 32 lanes that gives up (device printf + trap, i.e. a launch failure the host sees) instead of
+// spinning forever if the awaited bulk copy never completes.
+__device__ __forceinline__ void tp_wait(uint32_t bar, uint32_t parity, int code) {
+    unsigned spins = 0;
+    while (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
+        if (++spins > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0) printf("ssnt_tts_c: tp kernel wait %d timed out (block %d)\n", code, (int)blockIdx.x);
+            __trap();
+        }
+    }
+}
+
+// 2^dd for dd <= 0 as an exact float; 0 below the normal range (flush).
+__device__ __forceinline__ float tp_pow2_neg(int dd) {
+    return __int_as_float(max(dd + 127, 0) << 23);
+}
+// 2^dd for dd in [-127, 127]; 0 below, clamped above.
+__device__ __forceinline__ float tp_pow2(int dd) {
+    return __int_as_float(min(max(dd + 127, 0), 254) << 23);
+}
+
+template <int CPL>
+__device__ __forceinline__ void tp_load(const float* p, float (&v)[CPL]) {
+    if constexpr (CPL >= 4) {
+#pragma unroll
+        for (int q = 0; q < CPL / 4; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(p + 4 * q);
+            v[4 * q + 0] = w.x; v[4 * q + 1] = w.y; v[4 * q + 2] = w.z; v[4 * q + 3] = w.w;
+        }
+    } else {
+        const float2 w = *reinterpret_cast<const float2*>(p);
+        v[0] = w.x; v[1] = w.y;
+    }
+}
+template <int CPL>
+__device__ __forceinline__ void tp_store(float* p, const float (&v)[CPL]) {
+    if constexpr (CPL >= 4) {
+#pragma unroll
+        for (int q = 0; q < CPL / 4; ++q)
+            *reinterpret_cast<float4*>(p + 4 * q) = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+}
+
+// One lattice row of a chunk as probabilities, from the raw log-prob rows in shared memory.
+// Frames t >= T act as the identity (e = 1, s = 0) so that the virtual terminal vector passes through
+// a partial last chunk unchanged; tokens >= U and the prohibited shifts (last token, last frame) are 0.
+template <int CPL>
+__device__ __forceinline__ void tp_row_probs(const float* se, const float* ss, int l, int t, int T, int U, int max_u,
+                                             int c0, float (&e)[CPL], float (&s)[CPL]) {
+    if (t < T) {
+        float re[CPL], rs[CPL];
+        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, re);
+        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, rs);
+        const bool last = t == T - 1;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            e[r] = (c0 + r < U) ? ex2(to_log2(re[r])) : 0.0f;
+            s[r] = (c0 + r < U - 1 && !last) ? ex2(to_log2(rs[r])) : 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { e[r] = 1.0f; s[r] = 0.0f; }
+    }
+}
+
+// Starts the two bulk copies of a chunk's raw rows (lane 0 only) and returns after arming the barrier.
+__device__ __forceinline__ void tp_issue_chunk(const FbArgs& a, int b, int t0, int rows, float* se, float* ss, uint32_t bar) {
+    const size_t slab = (size_t)a.max_t * a.max_u;
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)a.max_u * 4u;
+    mbar_expect_tx(bar, 2u * bytes);
+    bulk_g2s(smem_u32(se), a.log_emit + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
+    bulk_g2s(smem_u32(ss), a.log_shift + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
+}
+
+__device__ __forceinline__ bool tp_lengths(const FbArgs& a, int b, int& T, int& U) {
+    T = a.t_len ? a.t_len[b] : a.max_t;
+    U = a.u_len ? a.u_len[b] : a.max_u;
+    T = min(max(T, 0), a.max_t);
+    U = min(max(U, 0), a.max_u);
+    return !(T <= 0 || U <= 0 || U > T);
+}
+
+// =================================================================================================
+// Kernel 1: chunk operators.
+// =================================================================================================
+template <int CPL, int L>
+__global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FbArgs& a = p.a;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
+    int T, U;
+    if (!tp_lengths(a, b, T, U)) return;
+    const int t0 = c * L;
+    if (t0 >= T) return;
+    const int max_u = a.max_u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* se = reinterpret_cast<float*>(smem_raw + 128);
+    float* ss = se + L * max_u;
+    if (lane == 0) {
+        mbar_init(smem_u32(bar), 1);
+        fence_mbar_init();
+        tp_issue_chunk(a, b, t0, min(L, a.max_t - t0), se, ss, smem_u32(bar));
+    }
+    __syncwarp();
+    const int c0 = lane * CPL;
+    const int src = (lane + 31) & 31;  // left neighbour, lane 0 wraps to lane 31 whose last shift is always 0
+
+    float Q[CPL][L + 1];
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        Q[r][0] = 1.0f;
+#pragma unroll
+        for (int d = 1; d <= L; ++d) Q[r][d] = 0.0f;
+    }
+    tp_wait(smem_u32(bar), 0, 1);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        float e[CPL], s[CPL];
+        tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+        // what enters this lane's first token from the left neighbour's last token, per diagonal
+        float X[L];
+#pragma unroll
+        for (int d = 0; d <= l; ++d) X[d] = __shfl_sync(kFull, s[CPL - 1] * Q[CPL - 1][d], src);
+#pragma unroll
+        for (int r = CPL - 1; r >= 1; --r) {
+            Q[r][l + 1] = s[r - 1] * Q[r - 1][l];
+#pragma unroll
+            for (int d = l; d >= 1; --d) Q[r][d] = fmaf(e[r], Q[r][d], s[r - 1] * Q[r - 1][d - 1]);
+            Q[r][0] = e[r] * Q[r][0];
+        }
+        Q[0][l + 1] = X[l];
+#pragma unroll
+        for (int d = l; d >= 1; --d) Q[0][d] = fmaf(e[0], Q[0][d], X[d - 1]);
+        Q[0][0] = e[0] * Q[0][0];
+    }
+    float* qg = p.Q + ((size_t)b * p.C + c) * (size_t)(L + 1) * p.UP + c0;
+#pragma unroll
+    for (int d = 0; d <= L; ++d) {
+        float w[CPL];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) w[r] = Q[r][d];
+        tp_store<CPL>(qg + (size_t)d * p.UP, w);
+    }
+}
+
+// =================================================================================================
+// Kernel 2: boundary vectors.  blockIdx.x = 2*b + dir (0 forward / alpha, 1 backward / beta); one thread per
+// token.  Step k multiplies the current vector (shared memory, zero-padded by L on both sides) by the k-th
+// operator of the sweep:  forward  y'(i) = sum_d Q(i,d) y(i-d),  backward  y'(j) = sum_d Q(j+d,d) y(j+d);
+// every shared-memory access is a conflict-free scalar load.
+//
+// Block float: one power-of-two exponent per warp (32 tokens).  A row's maximum can sit hundreds of bits above
+// the entries the other sweep will meet (beta piles up at token 0 long before alpha gets there), so one exponent
+// per row is not enough.  A thread's window reaches into one neighbouring warp only (L <= 32): it accumulates the
+// two warps' contributions separately, each in its source frame, and joins them with exact power-of-two factors.
+// The output frame of step k is predicted from the stored maxima of step k-1 plus the shrink observed one step
+// earlier (feedback, lag one), so no reduction sits on the step's dependency chain: one barrier per step.
+// =================================================================================================
+constexpr int kTpDead = -(1 << 20);  // frame of a warp whose tokens are all zero
+
+// NT compute threads (one per token) + one producer warp.  The producer issues the TMA copies of the operators
+// and waits for the next stage's mbarrier BEFORE it arrives at the step's CTA barrier, so the compute warps never
+// touch an mbarrier (a try_wait costs ~90 cycles even when the data has long landed).
+template <int NT, int L, int NS>
+__global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    static_assert(L <= 32, "a window must not reach beyond the neighbouring warp");
+    static_assert((NS & (NS - 1)) == 0 && NS <= 16, "ring size: power of two");
+    constexpr int VB = L + NT + L;  // one padded vector
+    constexpr int stage_floats = (L + 1) * NT;
+    const FbArgs& a = p.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x >> 1, dir = blockIdx.x & 1;
+    int T, U;
+    if (!tp_lengths(a, b, T, U)) return;
+    if (dir == 0 && tid == 0) p.status[b] = 0u;  // the fill kernel ORs into it
+    const int Cb = (T + L - 1) / L;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                  // [NS]
+    unsigned* wmax = reinterpret_cast<unsigned*>(smem_raw + 128);            // [2][8] warp maxima (float bits)
+    int* fsm = reinterpret_cast<int*>(smem_raw + 192);                       // [2][8] warp frames
+    float* vbuf = reinterpret_cast<float*>(smem_raw + 256);                  // [2][VB]
+    float* ring = vbuf + 2 * VB + ((4 - (2 * VB) % 4) % 4);                  // 16-byte aligned
+    const bool producer = tid >= NT;
+
+    if (producer) {
+        const float* qb = p.Q + (size_t)b * p.C * stage_floats;
+        auto issue = [&](int k) {
+            const int ck = dir == 0 ? k : Cb - 1 - k;
+            const int slot = k & (NS - 1);
+            const uint32_t bar = smem_u32(bars + slot);
+            mbar_expect_tx(bar, (uint32_t)stage_floats * 4u);
+            bulk_g2s(smem_u32(ring + (size_t)slot * stage_floats), qb + (size_t)ck * stage_floats, (uint32_t)stage_floats * 4u, bar);
+        };
+        if (lane == 0) {
+            for (int s = 0; s < NS; ++s) mbar_init(smem_u32(bars + s), 1);
+            fence_mbar_init();
+            for (int k = 0; k < min(NS, Cb); ++k) issue(k);
+        }
+        __syncwarp();
+        __syncthreads();  // S0 (pairs with the compute warps' set-up barrier)
+        tp_wait(smem_u32(bars), 0u, 2);
+        for (int k = 0; k < Cb; ++k) {
+            __syncthreads();  // B_k: every compute warp is done with stage k-1
+            if (lane == 0 && k >= 1 && k - 1 + NS < Cb) issue(k - 1 + NS);
+            if (k + 1 < Cb) tp_wait(smem_u32(bars + ((k + 1) & (NS - 1))), (unsigned)((k + 1) / NS) & 1u, 2);
+        }
+        return;
+    }
+
+    float* vec = (dir == 0 ? p.A : p.Bv) + (size_t)b * (p.C + 1) * (NT + 32);
+    const int hot0 = dir == 0 ? 0 : U - 1;
+    const int wn = dir == 0 ? warp - 1 : warp + 1;        // the neighbouring warp the window reaches into
+    const bool has_nb = wn >= 0 && wn < NT / 32;
+    const int wnc = has_nb ? wn : warp;
+    float y = tid == hot0 ? 1.0f : 0.0f;
+    int F = (hot0 >> 5) == warp ? 0 : kTpDead;  // this warp's frame (uniform within the warp)
+    int guess = 0;                              // shrink (exponent) observed one step earlier
+    for (int i = tid; i < 2 * VB; i += NT) vbuf[i] = 0.0f;
+    if (tid < 16) { wmax[tid] = 0u; fsm[tid] = kTpDead; }
+    __syncthreads();  // S0
+    vbuf[L + tid] = y;
+    if (lane == 0) {
+        wmax[warp] = F == 0 ? 0x3f800000u : 0u;  // the unit vector's maximum
+        fsm[warp] = F;
+    }
+    // global rows of the boundary vectors, walked in sweep order
+    const ptrdiff_t rstride = dir == 0 ? (NT + 32) : -(NT + 32);
+    float* row = vec + (size_t)(dir == 0 ? 0 : Cb) * (NT + 32);
+    row[tid] = y;
+    if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F;
+    // per-lane masks: which diagonals stay inside this warp
+    for (int k = 0; k < Cb; ++k) {
+        const int cur = k & 1;
+        __syncthreads();  // B_k: vector k, its warp maxima and frames are visible; stage k has landed (producer)
+        const float* q = ring + (size_t)(k & (NS - 1)) * stage_floats + tid;
+        const float* yv = vbuf + cur * VB + L + tid;
+        float s_own = 0.0f, s_own2 = 0.0f, s_nb = 0.0f, s_nb2 = 0.0f;
+        if (dir == 0) {
+#pragma unroll
+            for (int d = 0; d <= L; ++d) {
+                const float t = q[d * NT] * yv[-d];
+                if (d <= lane) { if (d & 1) s_own2 += t; else s_own += t; }
+                else { if (d & 1) s_nb2 += t; else s_nb += t; }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d <= L; ++d) {
+                const float qv = (tid + d < NT) ? q[d * NT + d] : 0.0f;
+                const float t = qv * yv[d];
+                if (lane + d <= 31) { if (d & 1) s_own2 += t; else s_own += t; }
+                else { if (d & 1) s_nb2 += t; else s_nb += t; }
+            }
+        }
+        // frames (independent of the sums above until the last line)
+        const unsigned mw = wmax[cur * 8 + warp];
+        const unsigned mn = has_nb ? wmax[cur * 8 + wnc] : 0u;
+        const int Fn = has_nb ? fsm[cur * 8 + wnc] : kTpDead;
+        const int sw = (int)(mw >> 23) - 127;
+        const int aw = mw ? F + sw : kTpDead;                             // absolute exponent of this warp's maximum
+        const int an = mn ? Fn + (int)(mn >> 23) - 127 : kTpDead;         // and of the neighbour's
+        // this warp's maximum sits 2^sw above the prediction made for it: the step before shrank by guess + sw
+        if (mw) guess = max(min(guess + sw, 0), -100);
+        int Fout = max(aw, an - 24);                  // what enters from the neighbour has been shifted at least once
+        Fout = Fout > kTpDead / 2 ? Fout + guess : kTpDead;
+        // y' = S_own 2^(F - Fout) + S_nb 2^(Fn - Fout); a factor beyond 2^126 means the prediction was far too low:
+        // raise the output frame so that the larger factor is exactly 2^126
+        const int top = max(F, Fn) - Fout;
+        if (Fout > kTpDead / 2 && top > 126) Fout += top - 126;
+        const float c_own = tp_pow2(F - Fout), c_nb = tp_pow2(Fn - Fout);
+        y = (s_own + s_own2) * c_own + (s_nb + s_nb2) * c_nb;
+        vbuf[(cur ^ 1) * VB + L + tid] = y;
+        const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(fmaxf(y, 0.0f)));
+        F = wm ? Fout : kTpDead;
+        if (lane == 0) {
+            wmax[(cur ^ 1) * 8 + warp] = wm;
+            fsm[(cur ^ 1) * 8 + warp] = F;
+        }
+        row += rstride;
+        row[tid] = y;
+        if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F;
+    }
+    // Z: forward = alpha_C(U-1) (beta_C is the unit vector there), backward = beta_0(0).
+    if (tid == (dir == 0 ? U - 1 : 0)) {
+        float* z = p.zlg + (size_t)b * 4 + dir * 2;
+        z[0] = y > 0.0f ? log2f(y) : -INFINITY;
+        z[1] = (float)F;
+    }
+}
+
+// =================================================================================================
+// Kernel 3: chunk interiors and gradients.
+// =================================================================================================
+template <int CPL, int L>
+__global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FbArgs& a = p.a;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
+    const int max_u = a.max_u, max_t = a.max_t, UP = p.UP;
+    const int c0 = lane * CPL;
+    const int t0 = c * L;
+    const size_t slab = (size_t)max_t * max_u;
+    float* ge = a.grad_emit + (size_t)b * slab;
+    float* gs = a.grad_shift + (size_t)b * slab;
+    const float zeros[CPL] = {};
+    auto zero_rows = [&](int from, int to) {
+        for (int t = from; t < to; ++t) {
+            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+        }
+    };
+    int T, U;
+    const int rows_end = min(t0 + L, max_t);
+    if (!tp_lengths(a, b, T, U)) {
+        zero_rows(t0, rows_end);
+        if (c == 0 && lane == 0) {
+            a.log_likelihood[b] = -INFINITY;
+            p.status[b] = 0u;
+        }
+        return;
+    }
+    // the two sweeps' likelihoods: (log2 mantissa, exponent)
+    const float* z = p.zlg + (size_t)b * 4;
+    const float zf_lg = z[0], zf_ex = z[1], zb_lg = z[2], zb_ex = z[3];
+    const float zdiff = (zf_ex - zb_ex) + (zf_lg - zb_lg);
+    const bool z_ok = (zf_lg > -1e30f) && (zb_lg > -1e30f) && fabsf(zdiff) <= kTpZTol && !p.force_fallback;
+    if (!z_ok) {
+        // no mass reached the end (a true -inf or an underflow) or the sweeps disagree: the log-domain kernel decides
+        if (c == 0 && lane == 0) p.status[b] = p.force_fallback ? (unsigned)kTpForced : (unsigned)kTpBadZ;
+#ifdef SSNT_TP_TRACE
+        if (c == 0 && lane == 0) printf("tp: b=%d bad Z: fwd %f + %f, bwd %f + %f, diff %g\n", b, zf_lg, zf_ex, zb_lg, zb_ex, zdiff);
+#endif
+        return;
+    }
+    if (t0 >= T) {
+        zero_rows(t0, rows_end);
+        return;
+    }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* se = reinterpret_cast<float*>(smem_raw + 128);
+    float* ss = se + L * max_u;
+    if (lane == 0) {
+        mbar_init(smem_u32(bar), 1);
+        fence_mbar_init();
+        tp_issue_chunk(a, b, t0, min(L, max_t - t0), se, ss, smem_u32(bar));
+    }
+    __syncwarp();
+    if (c == 0 && lane == 0) {
+        a.log_likelihood[b] = (float)(((double)zf_lg + (double)zf_ex) * kLn2);
+        // status[b] was zeroed by the combine kernel; a bad row below ORs into it
+    }
+    // boundary vectors and their per-lane exponents
+    const float* arow = p.A + ((size_t)b * (p.C + 1) + c) * (UP + 32);
+    const float* brow = p.Bv + ((size_t)b * (p.C + 1) + c + 1) * (UP + 32);
+    float av[CPL], bv[CPL];
+    tp_load<CPL>(arow + c0, av);
+    tp_load<CPL>(brow + c0, bv);
+    // one exponent per 32 tokens (the combine kernel's warps); this lane's CPL tokens lie in group lane*CPL/32
+    const int ea = reinterpret_cast<const int*>(arow + UP)[(lane * CPL) >> 5];
+    const int eb = reinterpret_cast<const int*>(brow + UP)[(lane * CPL) >> 5];
+    // Frames held fixed over the chunk, one per lane: F_l = max(ex_l, F_{l-1} - dec) for alpha (mass arrives from
+    // the left), F_l = max(ex_l, F_{l+1} - dec) for beta (from the right): a lane the front has not reached takes
+    // its neighbour's frame lowered by dec, so that what enters it within L rows neither overflows nor flushes.
+    constexpr int kDec = 96 / ((L + CPL - 1) / CPL);
+    int fa = ea + kDec * lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int other = __shfl_up_sync(kFull, fa, o);
+        if (lane >= o) fa = max(fa, other);
+    }
+    fa -= kDec * lane;
+    int fb = eb - kDec * lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int other = __shfl_down_sync(kFull, fb, o);
+        if (lane + o < 32) fb = max(fb, other);
+    }
+    fb += kDec * lane;
+    // (shuffles executed by all lanes, then selected: a shuffle under a lane-dependent condition is undefined)
+    const int fa_left = __shfl_up_sync(kFull, fa, 1), fb_right = __shfl_down_sync(kFull, fb, 1);
+    const float ka = lane == 0 ? 0.0f : tp_pow2(fa_left - fa);     // applied to what enters from lane-1
+    const float kb = lane == 31 ? 0.0f : tp_pow2(fb_right - fb);   // applied to what enters from lane+1
+    {
+        const float sa0 = tp_pow2_neg(ea - fa), sb0 = tp_pow2_neg(eb - fb);
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { av[r] *= sa0; bv[r] *= sb0; }
+    }
+    // occupancy = alpha * (e|s) * beta / Z = (a * 2^xa) * (p * 2^xb) with xa + xb = fa + fb - log2 Z, split evenly so
+    // that neither factor leaves the fp32 range before the product is formed
+    float sa, sb;
+    {
+        const float xi = (float)(fa + fb) - zf_ex;     // integers: exact
+        const float half = floorf(0.5f * xi);
+        sa = ex2(fminf(fmaxf((xi - half) - zf_lg, -126.0f), 126.0f));
+        sb = ex2(fminf(fmaxf(half, -126.0f), 126.0f));
+    }
+
+    tp_wait(smem_u32(bar), 0, 3);
+    // ---- alpha forward: rows 0..L-1 of the chunk kept in registers (scaled by sa); probabilities written back ----
+    float ar[L][CPL];
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        float e[CPL], s[CPL];
+        tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+        store_cells<CPL>(se + l * max_u, c0, max_u, e);  // the raw rows are overwritten in place by the probabilities
+        store_cells<CPL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) ar[l][r] = av[r] * sa;
+        if (l < L - 1) {
+            const float in = __shfl_up_sync(kFull, s[CPL - 1] * av[CPL - 1], 1) * ka;
+#pragma unroll
+            for (int r = CPL - 1; r >= 1; --r) av[r] = fmaf(e[r], av[r], s[r - 1] * av[r - 1]);
+            av[0] = fmaf(e[0], av[0], in);
+        }
+    }
+    __syncwarp();
+    // ---- beta backward with the gradients fused ----
+    float worst = 0.0f;
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+        const int t = t0 + l;
+        float e[CPL], s[CPL];
+        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
+        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+        const float bin = __shfl_down_sync(kFull, bv[0], 1) * kb;
+        float g1[CPL], g2[CPL];
+        float rowsum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            const float p1 = e[r] * bv[r];
+            const float p2 = s[r] * (r + 1 < CPL ? bv[r + 1] : bin);
+            g1[r] = ar[l][r] * (p1 * sb);
+            g2[r] = ar[l][r] * (p2 * sb);
+            rowsum += g1[r] + g2[r];
+            bv[r] = p1 + p2;
+        }
+        if (t < T) {
+            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
+            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+            rowsum = warp_sum(rowsum);
+            const float dev = fabsf(rowsum - 1.0f);
+            worst = (dev <= kTpRowTol) ? worst : 1.0f;  // also catches NaN
+#ifdef SSNT_TP_TRACE
+            if (!(dev <= kTpRowTol) && lane == 0) printf("tp: b=%d t=%d row sum %g (fa %d fb %d sa %g sb %g)\n", b, t, rowsum, fa, fb, sa, sb);
+#endif
+        } else if (t < max_t) {
+            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+        }
+    }
+    if (worst != 0.0f && lane == 0) atomicOr(p.status + b, (unsigned)kTpBadRow);
+}
+
+}  // namespace lattice
+}  // namespace ssnt

@@ -71,7 +71,7 @@ def test_config1_B1_U32_T120(product, oracle_mod, space):
     _check(got, want)
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3])  # generic, log-warp, block-float, block-float + forced log re-run
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 6, 7])  # generic, log-warp, block-float, block-float + forced log re-run, time-parallel (+ forced re-run)
 @pytest.mark.parametrize("B,T,U", [(3, 1, 4), (2, 2, 4), (4, 3, 4), (5, 9, 8), (3, 17, 16), (2, 40, 36),
                                    (3, 64, 64), (2, 100, 128), (2, 70, 200), (1, 90, 260), (1, 600, 520)])
 def test_shapes_and_ragged_lengths(product, oracle_mod, kind, B, T, U):
@@ -108,8 +108,8 @@ def test_infeasible_empty_and_masked(product, oracle_mod):
     le[0, 3, 2] = -np.inf                            # a single forbidden cell is fine
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     assert np.isneginf(want[0][[1, 2, 3, 5]]).all() and np.isfinite(want[0][[0, 4]]).all()
-    for kind in (0, 1, 2, 3, 4, 5):
-        if kind >= 4:
+    for kind in (0, 1, 2, 3, 4, 5, 6, 7):
+        if kind in (4, 5):
             continue  # max_u = 8 here; the split-role kernel needs max_u in {64, 128, 256} (covered below)
         got, _ = _run(product, le, ls, t_len, u_len, "device", kind)
         _check(got, want, t_len, u_len)
@@ -130,7 +130,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)  # exactly U-1 shifts
 
 
-@pytest.mark.parametrize("kind", [1, 2, 4])
+@pytest.mark.parametrize("kind", [1, 2, 4, 6])
 def test_config2_ragged(product, oracle_mod, kind):
     le, ls = make_inputs(32, 800, 128, seed=77)
     t_len, u_len = ragged_lengths(32, 800, 128)
@@ -151,6 +151,23 @@ def test_block_float_accuracy_budget(product, oracle_mod):
     assert np.abs(ge - ge64).max() <= 1e-5 and np.abs(gs - gs64).max() <= 1e-5
 
 
+def test_time_parallel_kernels_config2_and_no_fallback(product, oracle_mod):
+    """Kind 6 (chunk transfer operators built concurrently, fb_tp.cuh) at the headline shape: parity with the
+    fp64 oracle at the block-float accuracy budget, per-frame invariants, and no log-domain re-run on typical inputs."""
+    le, ls = make_inputs(32, 800, 128, seed=4321)
+    want = oracle_mod.forward_backward(le, ls)
+    before = product.fb_fallback_count()
+    got, used = _run(product, le, ls, None, None, "device", 6)
+    assert used == 6
+    assert product.fb_fallback_count() == before
+    _check(got, want)
+    ll, loss, ge, gs = (_np(g) for g in got)
+    assert np.all(np.abs(ll - want[0]) <= 2e-6 * np.abs(want[0]))
+    assert np.abs(ge - want[2]).max() <= 1e-5 and np.abs(gs - want[3]).max() <= 1e-5
+    np.testing.assert_allclose((ge + gs).sum(axis=2), 1.0, atol=2e-4)
+    np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)
+
+
 def test_peaked_and_uniform_inputs(product, oracle_mod):
     """Inputs that stress the dynamic range: exactly uniform probabilities (binomial spread of
     alpha over hundreds of bits) and a sharply peaked, mostly-wrong model (log-probs of -30)."""
@@ -163,7 +180,7 @@ def test_peaked_and_uniform_inputs(product, oracle_mod):
     le[2], ls[2] = np.log(1e-10), np.log1p(-1e-10)        # model insists on shifting every frame
     le[3], ls[3] = np.log1p(-1e-6), np.log(1e-6)          # model never wants to shift
     want = oracle_mod.forward_backward(le, ls)
-    for kind in (0, 1, 2, 4):   # kinds 2 and 4 must notice what they cannot hold and re-run it in the log domain
+    for kind in (0, 1, 2, 4, 6):   # kinds 2, 4 and 6 must notice what they cannot hold and re-run it in the log domain
         got, _ = _run(product, le, ls, None, None, "device", kind)
         _check(got, want)
 
@@ -285,7 +302,7 @@ def test_tone_latent_infeasible(product, oracle_mod):
 
 # ---- split-role kernel (kind 4; kind 5 = 4 with the log-domain re-run forced) and wide lattices ----------------
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("kind", [2, 3, 4, 5])
+@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("B,T,U", [(3, 64, 64), (2, 9, 64), (5, 333, 128), (2, 801, 128), (3, 130, 128),
                                    (2, 700, 256), (1, 300, 256), (35, 200, 128)])
 def test_full_width_lattices_all_block_float_kernels(product, oracle_mod, kind, B, T, U):
@@ -313,7 +330,7 @@ def test_split_kernel_infeasible_and_masked(product, oracle_mod):
     ls[5, 40, :] = -np.inf                                 # no path at all → -inf
     le[0, 3, 2] = -np.inf
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
-    for kind in (2, 4, 5):
+    for kind in (2, 4, 5, 6, 7):
         got, used = _run(product, le, ls, t_len, u_len, "device", kind)
         assert used == kind
         _check(got, want, t_len, u_len)
