@@ -141,9 +141,11 @@ void ssnt_tts_synchronize(void);
  * 4 = tone-latent empty beam, 8 = back-trace index out of range. */
 unsigned ssnt_tts_last_error(void);
 /* Forward-backward kernel selection for tests/benchmarks: -1 auto, 0 generic, 1 log-domain
- * warp/TMA, 2 block-float fused (cluster of 2 CTAs per utterance; auto choice for large batches),
- * 3 = 2 with forced log re-run, 4 block-float split-role (cluster of 4 CTAs per utterance; auto
- * choice when the whole batch fits one wave, i.e. 4*B <= SMs - 16), 5 = 4 with forced log re-run. */
+ * warp/TMA, 2 block-float fused (cluster of 2 CTAs per utterance), 3 = 2 with forced log re-run,
+ * 4 block-float split-role (cluster of 4 CTAs per utterance), 5 = 4 with forced log re-run,
+ * 6 time-parallel block-float (chunk transfer operators built concurrently, banded mat-vec sweep
+ * over the chunk boundaries, chunk interiors filled independently; the auto choice whenever
+ * max_u % 4 == 0 and max_u <= 256), 7 = 6 with forced log re-run. */
 void ssnt_tts_set_fb_kernel(int kind);
 int ssnt_tts_get_fb_kernel_used(void);
 /* Cumulative number of utterances the block-float kernel had to re-run in the log domain

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
     int U = a.u_len ? a.u_len[b] : a.max_u;
     T = min(max(T, 0), a.max_t);
     U = min(max(U, 0), a.max_u);
+    if (p.only) tp_pdl_wait();  // launched as a dependent of the time-parallel kernels: wait for their status words
     if (p.only && p.only[b] == 0u) {
         // re-run mode: this utterance's block-float results stand
     } else if (T <= 0 || U <= 0 || U > T) {
@@ -299,7 +300,7 @@ __global__ void fb_generic_kernel(const GenericParams p) {
 }
 
 template <int CPL>
-void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream) {
+void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream, bool dependent = false) {
     static size_t configured = 48 * 1024;  // per instantiation: largest opt-in requested so far
     if (smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(fb_log_warp_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -310,13 +311,15 @@ void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream) {
     cfg.blockDim = dim3(32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // re-run after the time-parallel kernels
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = dependent ? 2 : 1;
     SSNT_CUDA(cudaLaunchKernelEx(&cfg, fb_log_warp_kernel<CPL>, p));
 }
 
@@ -374,20 +377,44 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     const size_t chunk_smem = 128 + (size_t)2 * L * a.max_u * sizeof(float);
     constexpr int NT = 32 * CPL;
     constexpr int NS = NT <= 128 ? 16 : 8;   // 139 KB of operators in flight per (utterance, direction)
-    const size_t ring_smem = 256 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
+    // Exponent granularity of the boundary vectors: a warp's 32 tokens for max_u <= 128; half a warp for wider
+    // lattices, whose long sweeps (T = 2000 at U = 256) lost ~1e-4 of the likelihood with 32-token groups.
+    constexpr int G = NT <= 128 ? 32 : 16;
+    const size_t ring_smem = 512 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
     static size_t configured = 48 * 1024;
     if (ring_smem > configured) {
-        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
         configured = ring_smem;
     }
     const unsigned tasks = (unsigned)a.batch_size * (unsigned)p.C;
     static const int stages = [] { const char* e = std::getenv("SSNT_TP_DEBUG_STAGES"); return e ? std::atoi(e) : 3; }();
-    if (stages >= 1) tp_build_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p);
+    TpParams pg = p;
+    pg.G = G;
+    const TpParams& p2 = pg;
+    if (stages >= 1) tp_build_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p2);
     SSNT_CUDA(cudaGetLastError());
-    if (stages >= 2) tp_combine_kernel<NT, L, NS><<<(unsigned)a.batch_size * 2u, NT + 32, ring_smem, stream>>>(p);
-    SSNT_CUDA(cudaGetLastError());
-    if (stages >= 3) tp_fill_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p);
-    SSNT_CUDA(cudaGetLastError());
+    // dependent launches: each kernel's CTAs start while its predecessor drains and block in griddepcontrol.wait
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = stream;
+    cfg.attrs = pdl;
+    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 5; }();  // tuning aid: 1 combine, 2 fill (measured slower: its 1600 CTAs crowd the combine CTAs), 4 re-run
+    cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
+    if (stages >= 2) {
+        cfg.gridDim = dim3((unsigned)a.batch_size * 2u);
+        cfg.blockDim = dim3(NT + 32);
+        cfg.dynamicSmemBytes = ring_smem;
+        SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_combine_kernel<NT, L, NS, G>, pg));
+    }
+    cfg.numAttrs = (pdl_mask & 2) ? 1 : 0;
+    if (stages >= 3) {
+        cfg.gridDim = dim3(tasks);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = chunk_smem;
+        SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L>, pg));
+    }
 }
 
 }  // namespace
@@ -473,9 +500,9 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
     const bool bf_ok = warp_ok && a.max_u <= 256;
     const bool split_ok = bf_ok && (a.max_u == 64 || a.max_u == 128 || a.max_u == 256);
     int kind = tls_force_kind;
-    // few utterances (one wave of 4-CTA clusters): the split-role kernel keeps the recursion SMs free of
-    // everything else; many utterances: the fused kernel needs half the SMs per utterance
-    if (kind < 0) kind = (split_ok && a.batch_size * 4 <= sm_count() - 16) ? 4 : bf_ok ? 2 : (warp_ok ? 1 : 0);
+    // the time-parallel kernels (kind 6) win at every batch size measured (B = 4 .. 512, U = 64 / 128 / 256); the
+    // single-kernel block-float paths (2: fused, 4: split-role) remain selectable
+    if (kind < 0) kind = bf_ok ? 6 : (warp_ok ? 1 : 0);
     if (kind == 6 || kind == 7) {
         TpLayout tl;
         SSNT_ASSERT(bf_ok && tp_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: time-parallel kernels forced on an unsupported shape");
@@ -493,6 +520,8 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         const size_t stage = (size_t)(kTpL + 1) * tl.UP * sizeof(float);
         int NS = (int)((size_t)(200 * 1024) / stage);
         p.NS = NS > 16 ? 16 : NS;
+        static const int k2dbg = [] { const char* e = std::getenv("SSNT_TP_DEBUG_K2"); return e ? std::atoi(e) : 0; }();
+        p.debug = k2dbg;
         p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
         if (tl.CPL == 2) launch_tp<2>(p, stream);
         else if (tl.CPL == 4) launch_tp<4>(p, stream);
@@ -512,9 +541,10 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         int LNS = (int)((latency_mode ? 192 * 1024 : 52 * 1024) / stage_bytes);
         lp.NS = LNS < 2 ? 2 : (LNS > 8 ? 8 : LNS);
         const size_t smem = 128 + (size_t)lp.NS * stage_bytes;
-        if (tl.CPL == 2) launch_warp<2>(lp, smem, stream);
-        else if (tl.CPL == 4) launch_warp<4>(lp, smem, stream);
-        else launch_warp<8>(lp, smem, stream);
+        static const bool pdl4 = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? (std::atoi(e) & 4) != 0 : true; }();
+        if (tl.CPL == 2) launch_warp<2>(lp, smem, stream, pdl4);
+        else if (tl.CPL == 4) launch_warp<4>(lp, smem, stream, pdl4);
+        else launch_warp<8>(lp, smem, stream, pdl4);
         return;
     }
     if (kind >= 4) SSNT_ASSERT(split_ok, "forward_backward: split kernel forced on an unsupported shape");

@@ -46,6 +46,8 @@ struct TpParams {
     int UP;            // padded token count = 32 * CPL
     int NS;            // combine ring stages
     int force_fallback;
+    int G;             // tokens per block-float exponent of the boundary vectors (16 or 32)
+    int debug;         // profiling aid (SSNT_TP_DEBUG_K2): see tp_combine_kernel; results are wrong when non-zero
 };
 
 // mbarrier wait by all 32 lanes that gives up (device printf + trap, i.e. a launch failure the host sees) instead of
@@ -59,6 +61,12 @@ __device__ __forceinline__ void tp_wait(uint32_t bar, uint32_t parity, int code)
         }
     }
 }
+
+// Programmatic dependent launch: the four kernels of one call are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs are launched (and run their prologue) while
+// its predecessor drains; tp_pdl_wait() blocks until the predecessor has completed and its writes are visible.
+__device__ __forceinline__ void tp_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void tp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // 2^dd for dd <= 0 as an exact float; 0 below the normal range (flush).
 __device__ __forceinline__ float tp_pow2_neg(int dd) {
@@ -141,6 +149,7 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
     const FbArgs& a = p.a;
     const int lane = threadIdx.x;
     const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
+    tp_pdl_trigger();  // the combine kernel's CTAs may be launched as soon as every build CTA has started
     int T, U;
     if (!tp_lengths(a, b, T, U)) return;
     const int t0 = c * L;
@@ -209,15 +218,144 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
 // The output frame of step k is predicted from the stored maxima of step k-1 plus the shrink observed one step
 // earlier (feedback, lag one), so no reduction sits on the step's dependency chain: one barrier per step.
 // =================================================================================================
-constexpr int kTpDead = -(1 << 20);  // frame of a warp whose tokens are all zero
+constexpr int kTpDead = -(1 << 20);  // frame of a group whose tokens are all zero
+
+// The compute warps' sweep (DIR 0 forward, 1 backward): one straight-line block per step.
+//
+// Frames run two steps ahead of the data: while step k multiplies vector k, the warp reads the maxima of vector k
+// (published before the barrier), extrapolates the frame of vector k+2 from the shrink it observed over the last step,
+// and derives the two power-of-two factors step k+1 will join its sums with.  The step's own dependency chain is then
+// window loads -> FMAs -> two multiplies by register factors -> store, maximum, barrier.
+template <int NT, int L, int NS, int G, int DIR>
+__device__ __forceinline__ void tp_combine_sweep(const TpParams& p, int b, int U, int Cb, unsigned* wmax, int* fsm,
+                                                 float* vbuf, const float* ring) {
+    constexpr int VB = L + NT + L;
+    constexpr int stage_floats = (L + 1) * NT;
+    // exponent groups of G tokens (a warp or half a warp): `warp`/`lane` below are the group and the position in it
+    constexpr int kTpGroup = G;
+    const int tid = threadIdx.x, lane = tid & (kTpGroup - 1), warp = tid / kTpGroup;
+    const bool upper = (tid & 16) != 0;                     // upper half-warp
+    float* vec = (DIR == 0 ? p.A : p.Bv) + (size_t)b * (p.C + 1) * (NT + 32);
+    const int hot0 = DIR == 0 ? 0 : U - 1;
+    const int wn = DIR == 0 ? warp - 1 : warp + 1;        // the neighbouring group the window reaches into
+    const bool has_nb = wn >= 0 && wn < NT / kTpGroup;
+    const int wnc = has_nb ? wn : warp;
+    const int wn2 = DIR == 0 ? warp - 2 : warp + 2;       // two groups away: its mass can arrive within two steps
+    const bool has_nb2 = (2 * L > G) && wn2 >= 0 && wn2 < NT / kTpGroup;  // (mass crosses at most 2L tokens in two steps)
+    const int wn2c = has_nb2 ? wn2 : warp;
+    const bool hot_w = (hot0 / kTpGroup) == warp, hot_n = has_nb && (hot0 / kTpGroup) == wn;
+    float y = tid == hot0 ? 1.0f : 0.0f;
+    // frames of vector 0 and 1 (no shrink known yet), by the same rule as in the loop
+    int F0 = hot_w ? 0 : kTpDead;                           // frame of vector k   (uniform within the warp)
+    int F1 = hot_w ? 0 : (hot_n ? -24 : kTpDead);           // frame of vector k+1
+    const int Fn0 = hot_n ? 0 : kTpDead;
+    float c_own = tp_pow2(F0 - F1), c_nb = tp_pow2(Fn0 - F1);   // factors of step 0
+    int a_prev = kTpDead;                                   // absolute exponent of this warp's maximum one vector ago
+    int shrink2 = 0;                                        // extrapolated shrink over two steps (exponent, <= 0)
+    for (int i = tid; i < 2 * VB; i += NT) vbuf[i] = 0.0f;
+    if (tid < 32) wmax[tid] = 0u;                           // [2][16]
+    if (tid < 64) fsm[tid] = kTpDead;                       // [4][16]
+    __syncthreads();  // S0
+    vbuf[L + tid] = y;
+    if (lane == 0) {
+        wmax[warp] = hot_w ? 0x3f800000u : 0u;  // the unit vector's maximum
+        fsm[warp] = F0;
+        fsm[16 + warp] = F1;
+    }
+    // global rows of the boundary vectors, walked in sweep order
+    const ptrdiff_t rstride = DIR == 0 ? (NT + 32) : -(NT + 32);
+    float* row = vec + (size_t)(DIR == 0 ? 0 : Cb) * (NT + 32);
+    row[tid] = y;
+    if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F0;
+    const float* ybase = vbuf + L + tid;
+    const float* qbase = ring + tid;
+#pragma unroll 1
+    for (int k = 0; k < Cb; ++k) {
+        const int cur = k & 1;
+        __syncthreads();  // B_k: vector k, its warp maxima and the frames up to k+1 are visible; stage k has landed
+        const unsigned mw = wmax[cur * 16 + warp];
+        const unsigned mn = wmax[cur * 16 + wnc];
+        const unsigned mn2 = wmax[cur * 16 + wn2c];
+        const int Fnk = fsm[(k & 3) * 16 + wnc];
+        const int Fn2k = fsm[(k & 3) * 16 + wn2c];
+        const int Fnk1 = fsm[((k + 1) & 3) * 16 + wnc];
+        const float* q = qbase + (size_t)(k & (NS - 1)) * stage_floats;
+        const float* yv = ybase + cur * VB;
+        float yw[L + 1], qw[L + 1];
+#pragma unroll
+        for (int d = 0; d <= L; ++d) {
+            if (DIR == 0) {
+                yw[d] = yv[-d];
+                qw[d] = q[d * NT];
+            } else {
+                yw[d] = yv[d];
+                qw[d] = (tid + d < NT) ? q[d * NT + d] : 0.0f;
+            }
+        }
+        float s_own = 0.0f, s_own2 = 0.0f, s_nb = 0.0f, s_nb2 = 0.0f;
+#pragma unroll
+        for (int d = 0; d <= L; ++d) {
+            if ((p.debug & 1) && d > 0) break;
+            const float t = qw[d] * yw[d];
+            const bool own = DIR == 0 ? (d <= lane) : (lane + d < kTpGroup);
+            if (own) { if (d & 1) s_own2 += t; else s_own += t; }
+            else { if (d & 1) s_nb2 += t; else s_nb += t; }
+        }
+        // vector k+1 in frame F1:  y' = S_own 2^(F0 - F1) + S_nb 2^(Fn0 - F1)
+        y = (s_own + s_own2) * c_own + (s_nb + s_nb2) * c_nb;
+        vbuf[(cur ^ 1) * VB + L + tid] = y;
+        // half-warp maxima as two full-warp reductions of masked values (a reduction over a run-time sub-mask compiles to a loop)
+        const unsigned ybits = __float_as_uint(fmaxf(y, 0.0f));
+        unsigned wm;
+        if constexpr (G == 32) {
+            wm = __reduce_max_sync(kFull, ybits);
+        } else {
+            const unsigned wm_lo = __reduce_max_sync(kFull, upper ? 0u : ybits);
+            const unsigned wm_hi = __reduce_max_sync(kFull, upper ? ybits : 0u);
+            wm = upper ? wm_hi : wm_lo;
+        }
+        // ---- off the chain: frame of vector k+2 and the factors of step k+1 ----
+        const int aw = mw ? F0 + (int)(mw >> 23) - 127 : kTpDead;                        // absolute exponent of this warp's maximum
+        const int an = (has_nb && mn) ? Fnk + (int)(mn >> 23) - 127 : kTpDead;           // and of the neighbour's
+        if (aw > kTpDead / 2 && a_prev > kTpDead / 2) shrink2 = 2 * max(min(aw - a_prev, 0), -100);
+        a_prev = aw;
+        const int an2 = (has_nb2 && mn2) ? Fn2k + (int)(mn2 >> 23) - 127 : kTpDead;      // and two groups away
+        // frame of vector k+2: what enters from the neighbours has been shifted at least once per group crossed
+        int F2 = max(max(aw, an - 24), an2 - 48);
+        F2 = F2 > kTpDead / 2 ? F2 + shrink2 : kTpDead;
+        const int Fn1 = has_nb ? Fnk1 : kTpDead;
+        // a factor beyond 2^126 means the extrapolation was far too low: raise the frame so that the larger is 2^126
+        const int top = max(F1, Fn1) - F2;
+        if (F2 > kTpDead / 2 && top > 126) F2 += top - 126;
+        c_own = tp_pow2(F1 - F2);
+        c_nb = tp_pow2(Fn1 - F2);
+        if (lane == 0) {
+            wmax[(cur ^ 1) * 16 + warp] = wm;
+            fsm[((k + 2) & 3) * 16 + warp] = F2;
+        }
+        row += rstride;
+        if (!(p.debug & 2)) {
+            row[tid] = y;
+            if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F1;
+        }
+        F0 = F1;
+        F1 = F2;
+    }
+    // Z: forward = alpha_C(U-1) (beta_C is the unit vector there), backward = beta_0(0).  (F0 is the last vector's frame.)
+    if (tid == (DIR == 0 ? U - 1 : 0)) {
+        float* z = p.zlg + (size_t)b * 4 + DIR * 2;
+        z[0] = y > 0.0f ? log2f(y) : -INFINITY;
+        z[1] = (float)F0;
+    }
+}
 
 // NT compute threads (one per token) + one producer warp.  The producer issues the TMA copies of the operators
 // and waits for the next stage's mbarrier BEFORE it arrives at the step's CTA barrier, so the compute warps never
 // touch an mbarrier (a try_wait costs ~90 cycles even when the data has long landed).
-template <int NT, int L, int NS>
+template <int NT, int L, int NS, int G>
 __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    static_assert(L <= 32, "a window must not reach beyond the neighbouring warp");
+    static_assert(L <= G && (G == 16 || G == 32), "a window must not reach beyond the neighbouring exponent group");
     static_assert((NS & (NS - 1)) == 0 && NS <= 16, "ring size: power of two");
     constexpr int VB = L + NT + L;  // one padded vector
     constexpr int stage_floats = (L + 1) * NT;
@@ -229,11 +367,12 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
     if (dir == 0 && tid == 0) p.status[b] = 0u;  // the fill kernel ORs into it
     const int Cb = (T + L - 1) / L;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                  // [NS]
-    unsigned* wmax = reinterpret_cast<unsigned*>(smem_raw + 128);            // [2][8] warp maxima (float bits)
-    int* fsm = reinterpret_cast<int*>(smem_raw + 192);                       // [2][8] warp frames
-    float* vbuf = reinterpret_cast<float*>(smem_raw + 256);                  // [2][VB]
+    unsigned* wmax = reinterpret_cast<unsigned*>(smem_raw + 128);            // [2][16] group maxima (float bits)
+    int* fsm = reinterpret_cast<int*>(smem_raw + 256);                       // [4][16] group frames of vectors k..k+3 (mod 4)
+    float* vbuf = reinterpret_cast<float*>(smem_raw + 512);                  // [2][VB]
     float* ring = vbuf + 2 * VB + ((4 - (2 * VB) % 4) % 4);                  // 16-byte aligned
     const bool producer = tid >= NT;
+    tp_pdl_trigger();  // the fill kernel's CTAs may be launched (they wait for this grid's completion before reading)
 
     if (producer) {
         const float* qb = p.Q + (size_t)b * p.C * stage_floats;
@@ -247,97 +386,23 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
         if (lane == 0) {
             for (int s = 0; s < NS; ++s) mbar_init(smem_u32(bars + s), 1);
             fence_mbar_init();
-            for (int k = 0; k < min(NS, Cb); ++k) issue(k);
         }
+        tp_pdl_wait();  // the build kernel has completed: its operators are visible
+        if (lane == 0)
+            for (int k = 0; k < min(NS, Cb); ++k) issue(k);
         __syncwarp();
         __syncthreads();  // S0 (pairs with the compute warps' set-up barrier)
         tp_wait(smem_u32(bars), 0u, 2);
         for (int k = 0; k < Cb; ++k) {
             __syncthreads();  // B_k: every compute warp is done with stage k-1
             if (lane == 0 && k >= 1 && k - 1 + NS < Cb) issue(k - 1 + NS);
-            if (k + 1 < Cb) tp_wait(smem_u32(bars + ((k + 1) & (NS - 1))), (unsigned)((k + 1) / NS) & 1u, 2);
+            if (k + 1 < Cb && !(p.debug & 4)) tp_wait(smem_u32(bars + ((k + 1) & (NS - 1))), (unsigned)((k + 1) / NS) & 1u, 2);
         }
         return;
     }
 
-    float* vec = (dir == 0 ? p.A : p.Bv) + (size_t)b * (p.C + 1) * (NT + 32);
-    const int hot0 = dir == 0 ? 0 : U - 1;
-    const int wn = dir == 0 ? warp - 1 : warp + 1;        // the neighbouring warp the window reaches into
-    const bool has_nb = wn >= 0 && wn < NT / 32;
-    const int wnc = has_nb ? wn : warp;
-    float y = tid == hot0 ? 1.0f : 0.0f;
-    int F = (hot0 >> 5) == warp ? 0 : kTpDead;  // this warp's frame (uniform within the warp)
-    int guess = 0;                              // shrink (exponent) observed one step earlier
-    for (int i = tid; i < 2 * VB; i += NT) vbuf[i] = 0.0f;
-    if (tid < 16) { wmax[tid] = 0u; fsm[tid] = kTpDead; }
-    __syncthreads();  // S0
-    vbuf[L + tid] = y;
-    if (lane == 0) {
-        wmax[warp] = F == 0 ? 0x3f800000u : 0u;  // the unit vector's maximum
-        fsm[warp] = F;
-    }
-    // global rows of the boundary vectors, walked in sweep order
-    const ptrdiff_t rstride = dir == 0 ? (NT + 32) : -(NT + 32);
-    float* row = vec + (size_t)(dir == 0 ? 0 : Cb) * (NT + 32);
-    row[tid] = y;
-    if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F;
-    // per-lane masks: which diagonals stay inside this warp
-    for (int k = 0; k < Cb; ++k) {
-        const int cur = k & 1;
-        __syncthreads();  // B_k: vector k, its warp maxima and frames are visible; stage k has landed (producer)
-        const float* q = ring + (size_t)(k & (NS - 1)) * stage_floats + tid;
-        const float* yv = vbuf + cur * VB + L + tid;
-        float s_own = 0.0f, s_own2 = 0.0f, s_nb = 0.0f, s_nb2 = 0.0f;
-        if (dir == 0) {
-#pragma unroll
-            for (int d = 0; d <= L; ++d) {
-                const float t = q[d * NT] * yv[-d];
-                if (d <= lane) { if (d & 1) s_own2 += t; else s_own += t; }
-                else { if (d & 1) s_nb2 += t; else s_nb += t; }
-            }
-        } else {
-#pragma unroll
-            for (int d = 0; d <= L; ++d) {
-                const float qv = (tid + d < NT) ? q[d * NT + d] : 0.0f;
-                const float t = qv * yv[d];
-                if (lane + d <= 31) { if (d & 1) s_own2 += t; else s_own += t; }
-                else { if (d & 1) s_nb2 += t; else s_nb += t; }
-            }
-        }
-        // frames (independent of the sums above until the last line)
-        const unsigned mw = wmax[cur * 8 + warp];
-        const unsigned mn = has_nb ? wmax[cur * 8 + wnc] : 0u;
-        const int Fn = has_nb ? fsm[cur * 8 + wnc] : kTpDead;
-        const int sw = (int)(mw >> 23) - 127;
-        const int aw = mw ? F + sw : kTpDead;                             // absolute exponent of this warp's maximum
-        const int an = mn ? Fn + (int)(mn >> 23) - 127 : kTpDead;         // and of the neighbour's
-        // this warp's maximum sits 2^sw above the prediction made for it: the step before shrank by guess + sw
-        if (mw) guess = max(min(guess + sw, 0), -100);
-        int Fout = max(aw, an - 24);                  // what enters from the neighbour has been shifted at least once
-        Fout = Fout > kTpDead / 2 ? Fout + guess : kTpDead;
-        // y' = S_own 2^(F - Fout) + S_nb 2^(Fn - Fout); a factor beyond 2^126 means the prediction was far too low:
-        // raise the output frame so that the larger factor is exactly 2^126
-        const int top = max(F, Fn) - Fout;
-        if (Fout > kTpDead / 2 && top > 126) Fout += top - 126;
-        const float c_own = tp_pow2(F - Fout), c_nb = tp_pow2(Fn - Fout);
-        y = (s_own + s_own2) * c_own + (s_nb + s_nb2) * c_nb;
-        vbuf[(cur ^ 1) * VB + L + tid] = y;
-        const unsigned wm = __reduce_max_sync(kFull, __float_as_uint(fmaxf(y, 0.0f)));
-        F = wm ? Fout : kTpDead;
-        if (lane == 0) {
-            wmax[(cur ^ 1) * 8 + warp] = wm;
-            fsm[(cur ^ 1) * 8 + warp] = F;
-        }
-        row += rstride;
-        row[tid] = y;
-        if (lane == 0) reinterpret_cast<int*>(row + NT)[warp] = F;
-    }
-    // Z: forward = alpha_C(U-1) (beta_C is the unit vector there), backward = beta_0(0).
-    if (tid == (dir == 0 ? U - 1 : 0)) {
-        float* z = p.zlg + (size_t)b * 4 + dir * 2;
-        z[0] = y > 0.0f ? log2f(y) : -INFINITY;
-        z[1] = (float)F;
-    }
+    if (dir == 0) tp_combine_sweep<NT, L, NS, G, 0>(p, b, U, Cb, wmax, fsm, vbuf, ring);
+    else tp_combine_sweep<NT, L, NS, G, 1>(p, b, U, Cb, wmax, fsm, vbuf, ring);
 }
 
 // =================================================================================================
@@ -364,6 +429,8 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     };
     int T, U;
     const int rows_end = min(t0 + L, max_t);
+    tp_pdl_trigger();  // the log-domain re-run kernel may be launched; it waits for this grid before reading status
+    tp_pdl_wait();     // the combine kernel has completed: boundary vectors, likelihoods and status are visible
     if (!tp_lengths(a, b, T, U)) {
         zero_rows(t0, rows_end);
         if (c == 0 && lane == 0) {
@@ -408,9 +475,23 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     float av[CPL], bv[CPL];
     tp_load<CPL>(arow + c0, av);
     tp_load<CPL>(brow + c0, bv);
-    // one exponent per 32 tokens (the combine kernel's warps); this lane's CPL tokens lie in group lane*CPL/32
-    const int ea = reinterpret_cast<const int*>(arow + UP)[(lane * CPL) >> 5];
-    const int eb = reinterpret_cast<const int*>(brow + UP)[(lane * CPL) >> 5];
+    // one exponent per G tokens (16 or 32, the combine kernel's choice); this lane's CPL tokens lie in group lane*CPL/G.
+    // Within a group the entries the other sweep meets can sit ~100 bits below the group's maximum (steep fronts at
+    // U = 256), so each lane first re-normalises its own CPL mantissas (exact power-of-two scaling).
+    int ea = reinterpret_cast<const int*>(arow + UP)[(lane * CPL) / p.G];
+    int eb = reinterpret_cast<const int*>(brow + UP)[(lane * CPL) / p.G];
+    {
+        float ma = av[0], mb = bv[0];
+#pragma unroll
+        for (int r = 1; r < CPL; ++r) { ma = fmaxf(ma, av[r]); mb = fmaxf(mb, bv[r]); }
+        const int sha = ma > 0.0f ? (int)((__float_as_uint(ma) >> 23) & 0xffu) - 127 : 0;
+        const int shb = mb > 0.0f ? (int)((__float_as_uint(mb) >> 23) & 0xffu) - 127 : 0;
+        const float fa0 = tp_pow2(-sha), fb0 = tp_pow2(-shb);
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { av[r] *= fa0; bv[r] *= fb0; }
+        ea = (ma > 0.0f && ea > kTpDead / 2) ? ea + sha : kTpDead;
+        eb = (mb > 0.0f && eb > kTpDead / 2) ? eb + shb : kTpDead;
+    }
     // Frames held fixed over the chunk, one per lane: F_l = max(ex_l, F_{l-1} - dec) for alpha (mass arrives from
     // the left), F_l = max(ex_l, F_{l+1} - dec) for beta (from the right): a lane the front has not reached takes
     // its neighbour's frame lowered by dec, so that what enters it within L rows neither overflows nor flushes.

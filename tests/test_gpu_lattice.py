@@ -67,7 +67,7 @@ def test_config1_B1_U32_T120(product, oracle_mod, space):
     le, ls = make_inputs(1, 120, 32, seed=1234)
     want = oracle_mod.forward_backward(le, ls)
     got, used = _run(product, le, ls, None, None, space)
-    assert used == 2  # the block-float hot-path kernel, not a fallback
+    assert used == 6  # the time-parallel block-float kernels, not a fallback
     _check(got, want)
 
 
@@ -95,7 +95,7 @@ def test_unaligned_max_u_takes_generic_kernel(product, oracle_mod, U):
     t_len, u_len = ragged_lengths(3, 47, U, seed=U)
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     got, used = _run(product, le, ls, t_len, u_len, "device")
-    assert used == (2 if U % 4 == 0 else 0)
+    assert used == (6 if U % 4 == 0 else 0)
     _check(got, want, t_len, u_len)
 
 
@@ -122,7 +122,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     le, ls = make_inputs(32, 800, 128, seed=1234)
     want = oracle_mod.forward_backward(le, ls)
     got, used = _run(product, le, ls, None, None, space)
-    assert used == 4  # B=32: the split-role block-float kernel (one cluster of four CTAs per utterance)
+    assert used == 6  # the time-parallel kernels (chunk operators / boundary vectors / chunk interiors)
     _check(got, want)
     ll, loss, ge, gs = (_np(g) for g in got)
     rows = (ge + gs).sum(axis=2)
@@ -338,9 +338,9 @@ def test_split_kernel_infeasible_and_masked(product, oracle_mod):
 
 @pytest.mark.timeout(120)
 def test_auto_dispatch_small_and_large_batches(product):
-    """Few utterances → split-role kernel (kind 4); more than one wave of 4-CTA clusters → fused kernel."""
+    """Every aligned shape up to max_u = 256 takes the time-parallel kernels (kind 6), whatever the batch size."""
     import torch
-    for B, want_kind in ((4, 4), (32, 4), (64, 2)):
+    for B, want_kind in ((4, 6), (32, 6), (64, 6), (300, 6)):
         z = torch.randn(B, 200, 128, device="cuda")
         le, ls = torch.nn.functional.logsigmoid(z), torch.nn.functional.logsigmoid(-z)
         ll, loss, ge, gs = product.forward_backward(le, ls)
