@@ -138,7 +138,8 @@ void ssnt_tts_set_memory_space(int space);
 void ssnt_tts_synchronize(void);
 /* Waits for the current stream, returns and clears the error bits without aborting:
  * 1 = v2 empty beam (src/v2.rs:292), 2 = upsample length mismatch (src/v2_util.rs:58),
- * 4 = tone-latent empty beam, 8 = back-trace index out of range. */
+ * 4 = tone-latent empty beam, 8 = back-trace index out of range, 16 = a peer never delivered
+ * its loss entry (loss exchange). */
 unsigned ssnt_tts_last_error(void);
 /* Forward-backward kernel selection for tests/benchmarks: -1 auto, 0 generic, 1 log-domain
  * warp/TMA, 2 block-float fused (cluster of 2 CTAs per utterance), 3 = 2 with forced log re-run,
@@ -155,6 +156,24 @@ unsigned ssnt_tts_fb_fallback_count(void);
  * cycle counters (total, and cycles blocked on each hand-off barrier); NULL switches it off. */
 void ssnt_tts_debug_set_fb_stats(void *dev_buffer);
 const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
+
+/* ------------------------------------------------------------------------------------------
+ * Block 4 — multi-GPU loss exchange (no counterpart in the reference, which is single-process).
+ * Utterances are independent, so N GPUs each take a batch shard (the reference's par_chunks over
+ * the batch, src/v2.rs:227); the one value that crosses GPUs is the scalar loss.  Once connected,
+ * the kernel that reduces a forward_backward call's loss also stores {loss, call number} into
+ * every rank's slot buffer with one 64-bit NVLink store per peer: nothing extra is launched, the
+ * host issues no collective, and the exchange replays with a CUDA graph that captured the call.
+ * Every rank must make the same sequence of loss-producing calls (device pointers, loss != NULL).
+ *   export   allocates this rank's slot buffer and returns its 64-byte CUDA IPC handle
+ *   connect  handles[world_size][64] gathered from all ranks (any transport), own included
+ *   allreduce  out[0] = sum over ranks of the latest call's loss (same bits on every rank);
+ *              waits, on the stream, for the peers' entries; host or device pointer
+ * ---------------------------------------------------------------------------------------- */
+void ssnt_tts_loss_exchange_export(int world_size, unsigned char *handle_out /* [64] */);
+void ssnt_tts_loss_exchange_connect(int rank, int world_size, const unsigned char *handles);
+void ssnt_tts_loss_exchange_disconnect(void);
+void ssnt_tts_loss_allreduce(float *out);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,8 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -50,24 +52,84 @@ int pool_size() {
     return n == 0 ? 1 : (int)n;
 }
 
+// Persistent worker pool (rayon's global pool is created once, too): the workers sleep on a condition
+// variable between calls, so a call does not pay for thread creation.
+class Pool {
+public:
+    explicit Pool(int n) {
+        for (int k = 0; k < n; ++k) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    void run(int n, const std::function<void(int)>& body) {
+        std::unique_lock<std::mutex> l(mu_);
+        body_ = &body;
+        n_ = n;
+        next_.store(0);
+        pending_ = (int)workers_.size();
+        ++epoch_;
+        cv_.notify_all();
+        done_.wait(l, [this] { return pending_ == 0; });
+        body_ = nullptr;
+    }
+
+private:
+    void loop() {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void(int)>* body;
+            int n;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+                body = body_;
+                n = n_;
+            }
+            for (;;) {
+                int i = next_.fetch_add(1);
+                if (i >= n) break;
+                (*body)(i);
+            }
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* body_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, pending_ = 0;
+    unsigned epoch_ = 0;
+    bool stop_ = false;
+};
+
+std::mutex g_pool_mu;     // one parallel_for at a time (callers are the single-threaded tests / bench)
+Pool* g_pool = nullptr;   // intentionally leaked at exit: workers must not be joined from a static destructor
+
 void parallel_for(int n, const std::function<void(int)>& body) {
-    int nt = std::min(pool_size(), n);
-    if (nt <= 1) {
+    const int want = pool_size();
+    if (want <= 1 || n <= 1) {
         for (int i = 0; i < n; ++i) body(i);
         return;
     }
-    std::atomic<int> next(0);
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (int k = 0; k < nt; ++k)
-        th.emplace_back([&]() {
-            for (;;) {
-                int i = next.fetch_add(1);
-                if (i >= n) break;
-                body(i);
-            }
-        });
-    for (auto& t : th) t.join();
+    std::lock_guard<std::mutex> l(g_pool_mu);
+    if (!g_pool || g_pool->size() != want) {
+        delete g_pool;
+        g_pool = new Pool(want);
+    }
+    g_pool->run(n, body);
 }
 
 [[noreturn]] void rust_panic(const char* msg) {

@@ -50,6 +50,10 @@ C_SYMBOLS = (
     "ssnt_tts_fb_fallback_count",
     "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
+    "ssnt_tts_loss_exchange_export",
+    "ssnt_tts_loss_exchange_connect",
+    "ssnt_tts_loss_exchange_disconnect",
+    "ssnt_tts_loss_allreduce",
 )
 
 ERR_V2_EMPTY_BEAM = 1
@@ -365,3 +369,40 @@ def all_reduce_loss(loss, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     return loss
+
+
+def connect_loss_exchange(group=None) -> None:
+    """Connects the NVLink loss exchange of the C library across the ranks of the initialised
+    torch.distributed group (one process per GPU of one node): gathers every rank's CUDA IPC handle
+    and opens the peers' slot buffers.  Afterwards each device-pointer ``forward_backward`` /
+    ``tone_latent_forward_backward`` call also stores its loss into every rank's buffer from inside the
+    kernel that reduces it; ``loss_allreduce()`` returns the sum of the latest call."""
+    import torch.distributed as dist
+    torch = _torch()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = (ctypes.c_ubyte * 64)()
+    lib().ssnt_tts_loss_exchange_export(c_int(world), buf)
+    mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        mine = mine.cuda()
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    blob = b"".join(bytes(t.cpu().tolist()) for t in gathered)
+    handles = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(blob)
+    lib().ssnt_tts_loss_exchange_connect(c_int(rank), c_int(world), handles)
+    dist.barrier(group)  # nobody stores into a peer before every rank has connected
+
+
+def disconnect_loss_exchange() -> None:
+    lib().ssnt_tts_loss_exchange_disconnect()
+
+
+def loss_allreduce(out=None):
+    """Sum over ranks of the latest call's loss (the same bits on every rank), as a 1-element CUDA tensor;
+    asynchronous on torch's current stream."""
+    torch = _torch()
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device="cuda")
+    lib().ssnt_tts_set_stream(c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
+    lib().ssnt_tts_loss_allreduce(c_void_p(out.data_ptr()))
+    return out

@@ -90,6 +90,34 @@ struct AuxStreams {
 };
 thread_local AuxStreams tls_aux;
 
+// Host buffers of the reference's DEVICE_CPU callers are ordinary pageable allocations
+// (ssnt-tts-tensorflow/src/ssnt_tts_v2_beam_search_decode_op.cc:146-177 allocate_output).  A cudaMemcpyAsync on
+// pageable memory goes through the driver's bounce buffer and does not overlap with anything, so the lattice calls
+// page-lock the caller's large buffers IN PLACE for the duration of the call (cudaHostRegister; nothing is cached
+// across calls — a cached registration would dangle once the caller frees the buffer) and copy by DMA.
+// SSNT_HOST_REGISTER=0 switches this off (plain copies); buffers that are already pinned, are small, or cannot be
+// registered take the plain path.
+class HostPin {
+public:
+    ~HostPin() {
+        for (void* p : pinned_) cudaHostUnregister(p);
+        cudaGetLastError();
+    }
+    void add(const void* host, size_t bytes) {
+        static const bool enabled = [] { const char* e = std::getenv("SSNT_HOST_REGISTER"); return !e || std::atoi(e) != 0; }();
+        if (!enabled || !host || bytes < ((size_t)1 << 20) || is_pinned_host_pointer(host)) return;
+        // whole pages: round the range outwards (registering a neighbour's page as well is harmless)
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(host) & ~(uintptr_t)4095;
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(host) + bytes + 4095) & ~(uintptr_t)4095;
+        if (cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterDefault) == cudaSuccess)
+            pinned_.push_back(reinterpret_cast<void*>(lo));
+        else
+            cudaGetLastError();  // e.g. overlaps a range somebody else registered: plain copies still work
+    }
+private:
+    std::vector<void*> pinned_;
+};
+
 }  // namespace
 }  // namespace ssnt
 
@@ -279,6 +307,11 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
     // critical path of a ~0.7 ms call, hence no events and one download of the likelihoods at the end.
     const size_t slab = n2(max_t, max_u);
     const int B = batch_size > 0 ? batch_size : 0;
+    HostPin pin;  // unregisters when the call returns (every copy has completed by then)
+    pin.add(log_emit, B * slab * sizeof(float));
+    pin.add(log_shift, B * slab * sizeof(float));
+    pin.add(grad_emit, B * slab * sizeof(float));
+    pin.add(grad_shift, B * slab * sizeof(float));
     float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
     float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
     float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
@@ -288,9 +321,9 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
     int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
     int nchunks = 1;
     if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 8 ? 4 : 2;  // measured: 4 chunks 0.82 ms, 6: 0.86, 8: 0.89 (cfg2; PCIe floor ~0.6)
-    if (const char* e = std::getenv("SSNT_FB_CHUNKS")) {  // tuning aid
-        nchunks = std::atoi(e);
-        nchunks = nchunks < 1 ? 1 : (nchunks > kMaxChunks ? kMaxChunks : nchunks);
+    static const int env_chunks = [] { const char* e = std::getenv("SSNT_FB_CHUNKS"); return e ? std::atoi(e) : 0; }();  // tuning aid
+    if (env_chunks > 0) {
+        nchunks = env_chunks > kMaxChunks ? kMaxChunks : env_chunks;
         if (nchunks > B) nchunks = B > 0 ? B : 1;
     }
     const int per = (B + nchunks - 1) / (nchunks > 0 ? nchunks : 1);
@@ -347,6 +380,11 @@ void tone_latent_forward_backward(const float* log_emit, const float* log_shift,
     const int K = tone_class_size > 0 ? tone_class_size : 0;
     const int B = batch_size > 0 ? batch_size : 0;
     const size_t slab = n2(max_t, max_u) * (size_t)K, tslab = n2(max_u, K);
+    HostPin pin;
+    pin.add(log_emit, B * slab * sizeof(float));
+    pin.add(log_shift, B * slab * sizeof(float));
+    pin.add(grad_emit, B * slab * sizeof(float));
+    pin.add(grad_shift, B * slab * sizeof(float));
     float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
     float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
     float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
@@ -359,9 +397,9 @@ void tone_latent_forward_backward(const float* log_emit, const float* log_shift,
     int nchunks = 1;
     // measured on config 3 (2 x 105 MB): 2 chunks 3.26 ms, 4: 3.06, 6: 2.81, 8: 3.02 (unchunked 4.04)
     if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 12 ? 6 : (B >= 8 ? 4 : 2);
-    if (const char* e = std::getenv("SSNT_FB_CHUNKS")) {  // tuning aid
-        nchunks = std::atoi(e);
-        nchunks = nchunks < 1 ? 1 : (nchunks > kMaxChunks ? kMaxChunks : nchunks);
+    static const int env_chunks = [] { const char* e = std::getenv("SSNT_FB_CHUNKS"); return e ? std::atoi(e) : 0; }();  // tuning aid
+    if (env_chunks > 0) {
+        nchunks = env_chunks > kMaxChunks ? kMaxChunks : env_chunks;
         if (nchunks > B) nchunks = B > 0 ? B : 1;
     }
     const int per = (B + nchunks - 1) / nchunks;
@@ -425,6 +463,29 @@ unsigned ssnt_tts_fb_fallback_count(void) {
     return read_fallback_counter();
 }
 const char* ssnt_tts_backend(void) { return "cuda-sm_100a"; }
+
+// ---- multi-GPU loss exchange (batch-sharded training) ---------------------------------------------
+void ssnt_tts_loss_exchange_export(int world_size, unsigned char* handle_out) {
+    NOT_NULL(handle_out);
+    loss_exchange_export(world_size, handle_out);
+}
+void ssnt_tts_loss_exchange_connect(int rank, int world_size, const unsigned char* handles) {
+    NOT_NULL(handles);
+    loss_exchange_connect(rank, world_size, handles);
+}
+void ssnt_tts_loss_exchange_disconnect(void) { loss_exchange_disconnect(); }
+void ssnt_tts_loss_allreduce(float* out) {
+    NOT_NULL(out);
+    if (is_device_pointer(out)) {
+        launch_loss_allreduce(out, current_stream());
+        return;
+    }
+    float* d = (float*)device_scratch(39, sizeof(float));
+    launch_loss_allreduce(d, current_stream());
+    SSNT_CUDA(cudaMemcpyAsync(out, d, sizeof(float), cudaMemcpyDeviceToHost, current_stream()));
+    SSNT_CUDA(cudaStreamSynchronize(current_stream()));
+    check_error_flag_or_panic();
+}
 
 }  // extern "C"
 #pragma GCC visibility pop

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
         log_lattice_cta<CPL>(p, b, rank, lane, T, U, reinterpret_cast<uint64_t*>(smem_raw),
                              reinterpret_cast<float*>(smem_raw + 128), cluster);
     }
-    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, lane, 32);
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, lane, 32, a.xchg);
 }
 
 // MINB = 2: throughput variant, two CTAs (of different utterances) per SM — 128 registers per thread and
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBfThreads, MINB) fb_bf_kernel(const BfParams 
             }
         }
     }
-    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kBfThreads);
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kBfThreads, a.xchg);
 }
 
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) fb_split_kernel(const SplitP
             }
         }
     }
-    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kSplitThreads);
+    if (rank == 0) finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, kSplitThreads, a.xchg);
     if (tl && tid == 0) tl[3] = gtime();
 }
 
@@ -219,7 +219,7 @@ __global__ void fb_generic_kernel(const GenericParams p) {
     if (T <= 0 || U <= 0 || U > T) {
         for (size_t i = tid; i < slab; i += nt) { ge[i] = 0.0f; gs[i] = 0.0f; }
         if (tid == 0) a.log_likelihood[b] = -INFINITY;
-        finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, nt);
+        finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, nt, a.xchg);
         return;
     }
     // four rows of (max_u + 2) floats with a guard cell on each side: index u+1 <-> token u
@@ -296,12 +296,14 @@ __global__ void fb_generic_kernel(const GenericParams p) {
         tmp = co; co = no; no = tmp;
     }
     for (size_t i = (size_t)T * max_u + tid; i < slab; i += nt) { ge[i] = 0.0f; gs[i] = 0.0f; }
-    finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, nt);
+    finish_loss(a.log_likelihood, a.loss, a.batch_size, p.counter, tid, nt, a.xchg);
 }
 
 template <int CPL>
 void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream, bool dependent = false) {
-    static size_t configured = 48 * 1024;  // per instantiation: largest opt-in requested so far
+    static size_t configured_[64] = {};  // per instantiation and device: largest opt-in requested so far
+    size_t& configured = configured_[device_ordinal()];
+    if (configured == 0) configured = 48 * 1024;
     if (smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(fb_log_warp_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -325,7 +327,9 @@ void launch_warp(const LogParams& p, size_t smem, cudaStream_t stream, bool depe
 
 template <int CPL, int MINB = 1>
 void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
-    static size_t configured = 48 * 1024;
+    static size_t configured_[64] = {};  // per device
+    size_t& configured = configured_[device_ordinal()];
+    if (configured == 0) configured = 48 * 1024;
     if (smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(fb_bf_kernel<CPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -347,7 +351,9 @@ void launch_bf(const BfParams& p, size_t smem, cudaStream_t stream) {
 
 template <int CPL>
 void launch_split(const SplitParams& p, size_t smem, cudaStream_t stream) {
-    static size_t configured = 48 * 1024;
+    static size_t configured_[64] = {};  // per device
+    size_t& configured = configured_[device_ordinal()];
+    if (configured == 0) configured = 48 * 1024;
     if (smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(fb_split_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -381,13 +387,19 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     // lattices, whose long sweeps (T = 2000 at U = 256) lost ~1e-4 of the likelihood with 32-token groups.
     constexpr int G = NT <= 128 ? 32 : 16;
     const size_t ring_smem = 512 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
-    static size_t configured = 48 * 1024;
+    static size_t configured_[64] = {};  // per device
+    size_t& configured = configured_[device_ordinal()];
+    if (configured == 0) configured = 48 * 1024;
     if (ring_smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
         configured = ring_smem;
     }
     const unsigned tasks = (unsigned)a.batch_size * (unsigned)p.C;
+#ifdef SSNT_BF_DEBUG_VARIANTS  // stop after the first n kernels (profiling aid; results are incomplete)
     static const int stages = [] { const char* e = std::getenv("SSNT_TP_DEBUG_STAGES"); return e ? std::atoi(e) : 3; }();
+#else
+    constexpr int stages = 3;
+#endif
     TpParams pg = p;
     pg.G = G;
     const TpParams& p2 = pg;
@@ -444,6 +456,7 @@ static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
 // Split kernel (kind 4): state rows A [B][2][nstp*8][SU] (both sweeps, sweep order) and status [B].
 static size_t split_workspace_bytes(int B, int max_t, int max_u) {
     if (max_u != 64 && max_u != 128 && max_u != 256) return 0;
+    if (B > 64) return 0;  // one wave of 4-CTA clusters only: never taken (nor forced in a test) for larger batches
     const size_t SU = (size_t)max_u + 32;
     const size_t nstp = ((size_t)max_t + kG - 1) / kG;
     const size_t A = (size_t)B * 2 * nstp * kG * SU * sizeof(float);
@@ -470,7 +483,9 @@ void fb_set_stats_buffer(long long* dev) { tls_stats = dev; }
 long long* fb_get_stats_buffer() { return tls_stats; }
 void fb_force_kernel_kind(int kind) { tls_force_kind = kind; }
 
-void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
+void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
+    FbArgs a = a_in;
+    a.xchg = loss_exchange_device();  // multi-GPU: the loss reduction also stores into the peers' slot buffers
     if (a.batch_size <= 0) {
         if (a.loss) SSNT_CUDA(cudaMemsetAsync(a.loss, 0, sizeof(float), stream));
         return;
@@ -491,7 +506,7 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
     } else {
         ws = device_scratch(0, need);
     }
-    unsigned* counter = next_done_counter();
+    unsigned* counter = done_counter_for(ws);
 
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     bool warp_ok = (a.max_u % 4 == 0) && a.max_u <= 1024 && aligned16(a.log_emit) &&
@@ -520,15 +535,20 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         const size_t stage = (size_t)(kTpL + 1) * tl.UP * sizeof(float);
         int NS = (int)((size_t)(200 * 1024) / stage);
         p.NS = NS > 16 ? 16 : NS;
+        p.debug = 0;
+#ifdef SSNT_BF_DEBUG_VARIANTS
         static const int k2dbg = [] { const char* e = std::getenv("SSNT_TP_DEBUG_K2"); return e ? std::atoi(e) : 0; }();
         p.debug = k2dbg;
+#endif
         p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
         if (tl.CPL == 2) launch_tp<2>(p, stream);
         else if (tl.CPL == 4) launch_tp<4>(p, stream);
         else launch_tp<8>(p, stream);
         // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
+#ifdef SSNT_BF_DEBUG_VARIANTS
         static const bool skip_log = [] { const char* e = std::getenv("SSNT_TP_DEBUG_STAGES"); return e && std::atoi(e) < 4; }();
         if (skip_log) return;
+#endif
         LogParams lp;
         lp.a = a;
         lp.scratch = (float*)ws;
@@ -547,7 +567,7 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         else launch_warp<8>(lp, smem, stream, pdl4);
         return;
     }
-    if (kind >= 4) SSNT_ASSERT(split_ok, "forward_backward: split kernel forced on an unsupported shape");
+    if (kind >= 4) SSNT_ASSERT(split_ok && a.batch_size <= 64, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");
     tls_last_kind = kind;
@@ -563,7 +583,10 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         p.fallbacks = device_fallback_counter();
         p.force_fallback = kind == 5 ? 1 : 0;  // kind 5: run the split kernel but force the log-domain re-run
         p.debug = 0;
-        if (const char* e = std::getenv("SSNT_SPLIT_DEBUG")) p.debug = std::atoi(e);  // profiling aid
+#ifdef SSNT_BF_DEBUG_VARIANTS  // result-altering profiling knobs exist in debug builds only
+        static const int split_debug = [] { const char* e = std::getenv("SSNT_SPLIT_DEBUG"); return e ? std::atoi(e) : 0; }();
+        p.debug = split_debug;
+#endif
         p.counter = counter;
         p.stats = tls_stats;
         const size_t slot_bytes = ((size_t)2 * kG * a.max_u) * sizeof(float);
@@ -598,17 +621,23 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         // in the recursion and the helpers are the bottleneck anyway: 86 vs 106 G cells/s.
         bool two_per_sm = (size_t)a.batch_size * 2 > (size_t)sm_count() && a.max_u <= 64 &&
                           kBfHeaderBytes + 6 * stage_bytes <= 112 * 1024;
-        if (const char* e = std::getenv("SSNT_BF_TWO_PER_SM")) two_per_sm = two_per_sm && std::atoi(e) != 0;  // tuning aid
+        static const int env_two = [] { const char* e = std::getenv("SSNT_BF_TWO_PER_SM"); return e ? std::atoi(e) : 1; }();  // tuning aid
+        two_per_sm = two_per_sm && env_two != 0;
         if (two_per_sm) NS = 6;
         p.NS = NS;
         // Few utterances (latency mode): one CTA per SM has to cover the whole HBM latency by
         // itself, so prefetch far ahead; many utterances: neighbours share the L2, stay modest.
         p.pf_rows = (size_t)a.batch_size * 2 <= (size_t)sm_count() ? 256 : 64;
-        if (const char* e = std::getenv("SSNT_BF_PF_ROWS")) p.pf_rows = std::atoi(e);  // tuning aid
+        static const int env_pf = [] { const char* e = std::getenv("SSNT_BF_PF_ROWS"); return e ? std::atoi(e) : -1; }();  // tuning aid
+        if (env_pf >= 0) p.pf_rows = env_pf;
         p.pf_sleep_ns = 64;
-        if (const char* e = std::getenv("SSNT_BF_SLEEP_NS")) p.pf_sleep_ns = std::atoi(e);  // tuning aid
+        static const int env_sleep = [] { const char* e = std::getenv("SSNT_BF_SLEEP_NS"); return e ? std::atoi(e) : -1; }();  // tuning aid
+        if (env_sleep >= 0) p.pf_sleep_ns = env_sleep;
         p.debug_skip = 0;
-        if (const char* e = std::getenv("SSNT_BF_DEBUG_SKIP")) p.debug_skip = std::atoi(e);  // profiling aid
+#ifdef SSNT_BF_DEBUG_VARIANTS
+        static const int env_skip = [] { const char* e = std::getenv("SSNT_BF_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
+        p.debug_skip = env_skip;
+#endif
         const size_t smem = kBfHeaderBytes + (size_t)NS * stage_bytes;
         const int U = a.max_u;
         if (two_per_sm) {
@@ -656,6 +685,43 @@ void launch_forward_backward(const FbArgs& a, cudaStream_t stream) {
         fb_generic_kernel<<<a.batch_size, threads, smem, stream>>>(p);
         SSNT_CUDA(cudaGetLastError());
     }
+}
+
+// ---- all-reduced loss of the latest call: the sum of the `world` entries the ranks' kernels stored here ------------
+namespace {
+__global__ void loss_allreduce_kernel(LossExchange* x, float* out, unsigned* err) {
+    const int lane = threadIdx.x;
+    const unsigned seq = *(volatile unsigned*)&x->seq;
+    const int world = x->world;
+    const unsigned long long* mine = x->peers[x->rank] + (size_t)(seq % (unsigned)kLossRing) * kLossMaxWorld;
+    float v = 0.0f;
+    bool ok = true;
+    if (lane < world) {
+        unsigned long long e = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(e) : "l"(mine + lane) : "memory");
+            if ((unsigned)(e >> 32) == seq) break;
+            if (++spins > (1u << 24)) { ok = false; break; }  // a peer never delivered (seconds): report, do not hang
+            __nanosleep(100);
+        }
+        v = __uint_as_float((unsigned)e);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    float acc = 0.0f;
+    for (int r = 0; r < world; ++r) acc += __shfl_sync(0xffffffffu, v, r);  // rank order: identical bits on every rank
+    if (lane == 0) {
+        *out = ok ? acc : __int_as_float(0x7fc00000);
+        if (!ok) atomicOr(err, (unsigned)kErrLossExchange);
+    }
+}
+}  // namespace
+
+void launch_loss_allreduce(float* out_device, cudaStream_t stream) {
+    LossExchange* x = loss_exchange_device();
+    SSNT_ASSERT(x != nullptr, "ssnt_tts_loss_allreduce: no loss exchange connected");
+    loss_allreduce_kernel<<<1, 32, 0, stream>>>(x, out_device, device_error_flag());
+    SSNT_CUDA(cudaGetLastError());
 }
 
 }  // namespace ssnt

@@ -1,9 +1,11 @@
-// Runtime plumbing behind the C-ABI: stream side channel, device error flag, pointer-space
-// detection and grow-only scratch.  The reference's functions are stateless and re-entrant
-// (SURVEY.md §8b); all state here is thread-local or immutable after first use so that the
-// same holds for this library.
+// Runtime plumbing behind the C-ABI: stream side channel, device error flag, pointer-space detection,
+// grow-only scratch, completion counters and the NVLink loss exchange.  The reference's functions are
+// stateless and re-entrant; all state here is thread-local, per device, or immutable after
+// first use so that the same holds for this library.
 #include <atomic>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "ssnt_common.cuh"
@@ -11,6 +13,9 @@
 namespace ssnt {
 
 namespace {
+constexpr int kMaxDevices = 64;
+constexpr int kSlots = 40;
+
 thread_local cudaStream_t tls_stream = nullptr;
 thread_local int tls_space = kAuto;
 
@@ -18,27 +23,56 @@ struct Scratch {
     void* ptr = nullptr;
     size_t cap = 0;
 };
-constexpr int kSlots = 40;
-thread_local Scratch tls_dev[kSlots];
-thread_local Scratch tls_pin[kSlots];
+// per host thread AND per device: a thread that switches devices gets separate blocks
+struct ThreadScratch {
+    Scratch dev[kSlots];
+    Scratch pin[kSlots];
+};
+thread_local ThreadScratch* tls_scratch[kMaxDevices] = {};
 
-std::once_flag g_flag_once;
-unsigned* g_flag_host = nullptr;  // mapped pinned word
-unsigned* g_flag_dev = nullptr;  // [0] error bits, [1] count of utterances re-run in the log domain
-int g_sm_count = 0;
-constexpr int kCounters = 1024;
-unsigned* g_counters = nullptr;  // device, zeroed once; each user resets its ticket to 0
-std::atomic<unsigned> g_next_counter{0};
+// State of one device, created on first use with that device current.
+struct DeviceState {
+    std::once_flag once;
+    unsigned* flag_host = nullptr;  // mapped pinned words: [0] error bits, [1] utterances re-run in the log domain
+    unsigned* flag_dev = nullptr;
+    int sm_count = 0;
+    // completion counters ("last CTA reduces the loss"): one 32-byte sector per workspace address, zero whenever no
+    // kernel using it is in flight (the last CTA hands it back zeroed).  Keyed by workspace so that a captured graph,
+    // which replays with its workspace, can never share a counter with an eager call on another buffer.
+    std::mutex mu;
+    std::unordered_map<const void*, unsigned*> counters;
+    std::vector<unsigned*> blocks;
+    size_t used_in_block = 0;
+    static constexpr size_t kPerBlock = 4096;
+    LossExchange* xchg_dev = nullptr;  // device copy of the exchange descriptor (null until connected)
+    LossExchange xchg_host{};
+    unsigned long long* xchg_local = nullptr;
+};
+DeviceState g_dev[kMaxDevices];
 
-void init_flag() {
-    SSNT_CUDA(cudaHostAlloc((void**)&g_flag_host, 4 * sizeof(unsigned), cudaHostAllocMapped));
-    g_flag_host[0] = g_flag_host[1] = g_flag_host[2] = g_flag_host[3] = 0;
-    SSNT_CUDA(cudaHostGetDevicePointer((void**)&g_flag_dev, g_flag_host, 0));
+int current_device() {
     int dev = 0;
     SSNT_CUDA(cudaGetDevice(&dev));
-    SSNT_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    SSNT_CUDA(cudaMalloc((void**)&g_counters, kCounters * 32));
-    SSNT_CUDA(cudaMemset(g_counters, 0, kCounters * 32));
+    SSNT_ASSERT(dev >= 0 && dev < kMaxDevices, "device ordinal out of range");
+    return dev;
+}
+
+DeviceState& state() {
+    const int dev = current_device();
+    DeviceState& s = g_dev[dev];
+    std::call_once(s.once, [&]() {
+        SSNT_CUDA(cudaHostAlloc((void**)&s.flag_host, 4 * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
+        s.flag_host[0] = s.flag_host[1] = s.flag_host[2] = s.flag_host[3] = 0;
+        SSNT_CUDA(cudaHostGetDevicePointer((void**)&s.flag_dev, s.flag_host, 0));
+        SSNT_CUDA(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    });
+    return s;
+}
+
+ThreadScratch& scratch() {
+    const int dev = current_device();
+    if (!tls_scratch[dev]) tls_scratch[dev] = new ThreadScratch();
+    return *tls_scratch[dev];
 }
 }  // namespace
 
@@ -46,36 +80,33 @@ cudaStream_t current_stream() { return tls_stream; }
 void set_stream(cudaStream_t s) { tls_stream = s; }
 void set_space(int s) { tls_space = s; }
 
-unsigned* device_error_flag() {
-    std::call_once(g_flag_once, init_flag);
-    return g_flag_dev;
-}
+unsigned* device_error_flag() { return state().flag_dev; }
+int sm_count() { return state().sm_count; }
+int device_ordinal() { return current_device(); }
+unsigned* device_fallback_counter() { return state().flag_dev + 1; }
+unsigned read_fallback_counter() { return ((volatile unsigned*)state().flag_host)[1]; }
 
-unsigned* next_done_counter() {
-    std::call_once(g_flag_once, init_flag);
-    unsigned i = g_next_counter.fetch_add(1) % kCounters;
-    return g_counters + (size_t)i * 8;  // one 32-byte sector per ticket
-}
-
-int sm_count() {
-    std::call_once(g_flag_once, init_flag);
-    return g_sm_count;
-}
-
-unsigned* device_fallback_counter() {
-    std::call_once(g_flag_once, init_flag);
-    return g_flag_dev + 1;
-}
-
-unsigned read_fallback_counter() {
-    std::call_once(g_flag_once, init_flag);
-    return ((volatile unsigned*)g_flag_host)[1];
+unsigned* done_counter_for(const void* workspace) {
+    DeviceState& s = state();
+    std::lock_guard<std::mutex> lock(s.mu);
+    auto it = s.counters.find(workspace);
+    if (it != s.counters.end()) return it->second;
+    if (s.blocks.empty() || s.used_in_block == DeviceState::kPerBlock) {
+        unsigned* blk = nullptr;
+        SSNT_CUDA(cudaMalloc((void**)&blk, DeviceState::kPerBlock * 32));
+        SSNT_CUDA(cudaMemset(blk, 0, DeviceState::kPerBlock * 32));
+        s.blocks.push_back(blk);
+        s.used_in_block = 0;
+    }
+    unsigned* c = s.blocks.back() + (s.used_in_block++) * 8;  // one 32-byte sector each
+    s.counters.emplace(workspace, c);
+    return c;
 }
 
 unsigned read_and_clear_error_flag() {
-    std::call_once(g_flag_once, init_flag);
-    unsigned v = *(volatile unsigned*)g_flag_host;
-    if (v) *(volatile unsigned*)g_flag_host = 0;
+    DeviceState& s = state();
+    unsigned v = *(volatile unsigned*)s.flag_host;
+    if (v) *(volatile unsigned*)s.flag_host = 0;
     return v;
 }
 
@@ -91,6 +122,8 @@ void check_error_flag_or_panic() {
               __FILE__, __LINE__);
     if (v & kErrToneEmptyBeam)
         panic("tone_latent beam search: empty candidate set (src/tone_latent.rs:199)", __FILE__, __LINE__);
+    if (v & kErrLossExchange)
+        panic("loss exchange: a peer rank did not deliver its loss (did every rank make the same calls?)", __FILE__, __LINE__);
     panic("back-trace: parent index out of range (slice index panic)", __FILE__, __LINE__);
 }
 
@@ -103,12 +136,28 @@ bool is_device_pointer(const void* p) {
         cudaGetLastError();
         return false;
     }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+        // one process may drive several GPUs, but a call's buffers must live on the current device
+        SSNT_ASSERT(at.device == current_device(),
+                    "device pointer belongs to another GPU than the current one (cudaSetDevice before the call)");
+        return true;
+    }
+    return false;
+}
+
+bool is_pinned_host_pointer(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
 }
 
 void* device_scratch(int slot, size_t bytes) {
     SSNT_ASSERT(slot >= 0 && slot < kSlots, "scratch slot");
-    Scratch& s = tls_dev[slot];
+    Scratch& s = scratch().dev[slot];
     if (bytes > s.cap) {
         if (s.ptr) {
             // Work that still uses the old block may be in flight on the current stream.
@@ -124,7 +173,7 @@ void* device_scratch(int slot, size_t bytes) {
 
 void* pinned_scratch(int slot, size_t bytes) {
     SSNT_ASSERT(slot >= 0 && slot < kSlots, "scratch slot");
-    Scratch& s = tls_pin[slot];
+    Scratch& s = scratch().pin[slot];
     if (bytes > s.cap) {
         if (s.ptr) {
             SSNT_CUDA(cudaStreamSynchronize(tls_stream));
@@ -136,5 +185,62 @@ void* pinned_scratch(int slot, size_t bytes) {
     }
     return s.ptr;
 }
+
+// ---- loss exchange over NVLink peer memory ---------------------------------------------------------------------
+// Every rank owns a slot buffer [kLossRing][world] of 8-byte entries {loss bits, sequence number}.  The kernel that
+// reduces a call's loss stores its entry into EVERY rank's buffer (its own included) with one 64-bit store per peer;
+// the sum of a call's `world` entries is the all-reduced loss.  Nothing is launched for it and the host issues no
+// collective: the exchange is replayed with the CUDA graph that holds the call.
+void loss_exchange_export(int world, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SSNT_ASSERT(world >= 1 && world <= kLossMaxWorld, "loss exchange: world size out of range");
+    DeviceState& s = state();
+    if (!s.xchg_local) {
+        const size_t bytes = (size_t)kLossRing * kLossMaxWorld * sizeof(unsigned long long);
+        SSNT_CUDA(cudaMalloc((void**)&s.xchg_local, bytes));
+        SSNT_CUDA(cudaMemset(s.xchg_local, 0, bytes));
+        SSNT_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    SSNT_CUDA(cudaIpcGetMemHandle(&h, s.xchg_local));
+    std::memcpy(handle_out, &h, 64);
+}
+
+void loss_exchange_connect(int rank, int world, const unsigned char* handles) {
+    SSNT_ASSERT(world >= 1 && world <= kLossMaxWorld && rank >= 0 && rank < world, "loss exchange: bad rank / world size");
+    DeviceState& s = state();
+    SSNT_ASSERT(s.xchg_local != nullptr, "loss exchange: call ssnt_tts_loss_exchange_export first");
+    LossExchange x{};
+    x.rank = rank;
+    x.world = world;
+    x.seq = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            x.peers[r] = s.xchg_local;
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)r * 64, 64);
+            void* p = nullptr;
+            SSNT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            x.peers[r] = (unsigned long long*)p;
+        }
+    }
+    if (!s.xchg_dev) SSNT_CUDA(cudaMalloc((void**)&s.xchg_dev, sizeof(LossExchange)));
+    SSNT_CUDA(cudaMemcpy(s.xchg_dev, &x, sizeof(x), cudaMemcpyHostToDevice));
+    s.xchg_host = x;
+}
+
+void loss_exchange_disconnect() {
+    DeviceState& s = state();
+    if (!s.xchg_dev) return;
+    SSNT_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < s.xchg_host.world; ++r)
+        if (r != s.xchg_host.rank && s.xchg_host.peers[r]) cudaIpcCloseMemHandle(s.xchg_host.peers[r]);
+    SSNT_CUDA(cudaFree(s.xchg_dev));
+    s.xchg_dev = nullptr;
+    s.xchg_host = LossExchange{};
+}
+
+LossExchange* loss_exchange_device() { return state().xchg_dev; }
 
 }  // namespace ssnt

@@ -34,13 +34,17 @@ enum ErrorBits : unsigned {
     kErrUpsampleLength = 2u,     // src/v2_util.rs:58 assert_eq!(upsampled.len(), output_length)
     kErrToneEmptyBeam = 4u,      // src/tone_latent.rs:199 `i % n_results` with n_results == 0
     kErrBadIndex = 8u,           // out-of-range parent index in a back-trace table
+    kErrLossExchange = 16u,      // a peer rank never delivered its loss entry (multi-GPU loss exchange)
 };
 
 // ---- runtime (runtime.cu) ------------------------------------------------------------------
 cudaStream_t current_stream();             // thread-local side channel, see ssnt_tts_set_stream
 void set_stream(cudaStream_t s);
 void set_space(int space);
-unsigned* next_done_counter();             // zero-initialised, self-resetting ticket (ring of 1024)
+// Completion counter of the kernels that run on `workspace`: zero whenever none of them is in flight (the last
+// CTA hands it back zeroed).  One per workspace address, so a replayed graph never shares one with another call.
+unsigned* done_counter_for(const void* workspace);
+int device_ordinal();                      // cudaGetDevice(), checked
 unsigned* device_error_flag();             // device pointer to the flag word
 unsigned read_and_clear_error_flag();      // host side; caller must have synchronised
 unsigned* device_fallback_counter();       // utterances the block-float kernel re-ran in the log domain
@@ -48,7 +52,22 @@ unsigned read_fallback_counter();          // host side, cumulative
 void check_error_flag_or_panic();          // panics with the reference's message if a bit is set
 
 enum MemSpace { kAuto = 0, kHost = 1, kDevice = 2 };
-bool is_device_pointer(const void* p);     // honours ssnt_tts_set_memory_space
+bool is_device_pointer(const void* p);     // honours ssnt_tts_set_memory_space; panics on a pointer of another GPU
+bool is_pinned_host_pointer(const void* p);  // page-locked host memory (cudaHostAlloc / cudaHostRegister)?
+
+// ---- loss exchange over NVLink peer memory (runtime.cu, lattice_common.cuh::finish_loss) ---------------------------
+constexpr int kLossMaxWorld = 16;  // ranks of one node
+constexpr int kLossRing = 1024;    // calls whose entries are kept (ranks may drift apart by that many calls)
+struct LossExchange {
+    int rank, world;
+    unsigned seq;                                 // calls completed so far (device side; advances under graph replay)
+    unsigned long long* peers[kLossMaxWorld];     // every rank's slot buffer [kLossRing][kLossMaxWorld] of {loss bits, seq}
+};
+void loss_exchange_export(int world, unsigned char handle_out[64]);
+void loss_exchange_connect(int rank, int world, const unsigned char* handles);
+void loss_exchange_disconnect();
+LossExchange* loss_exchange_device();      // null until connected
+void launch_loss_allreduce(float* out_device, cudaStream_t stream);
 
 // Grow-only per-thread device scratch (workspace the caller did not provide, staging of host
 // buffers).  Slots are independent so one call can hold several live buffers.
@@ -77,6 +96,7 @@ struct FbArgs {
     float* grad_shift;      // [B,T,U]
     void* workspace;
     size_t workspace_bytes;
+    struct LossExchange* xchg = nullptr;  // set by the launcher when a loss exchange is connected (multi-GPU)
 };
 size_t fb_workspace_bytes(int batch_size, int max_t, int max_u);
 void launch_forward_backward(const FbArgs& a, cudaStream_t stream);
@@ -101,6 +121,7 @@ struct ToneFbArgs {
     float* grad_tone;
     void* workspace;
     size_t workspace_bytes;
+    struct LossExchange* xchg = nullptr;
 };
 size_t tone_fb_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
 // block-float split-role tone kernel (tone_bf.cu): supported shapes, extra workspace, launch (returns the

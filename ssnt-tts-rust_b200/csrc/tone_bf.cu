@@ -705,7 +705,9 @@ __global__ void __launch_bounds__(kTThreads, 1) tone_split_kernel(const ToneBfPa
 
 template <int CPL, int K>
 void launch_tone_split(const ToneBfParams& p, size_t smem, cudaStream_t stream) {
-    static size_t configured = 48 * 1024;
+    static size_t configured_[64] = {};  // per device
+    size_t& configured = configured_[device_ordinal()];
+    if (configured == 0) configured = 48 * 1024;
     if (smem > configured) {
         SSNT_CUDA(cudaFuncSetAttribute(tone_split_kernel<CPL, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

@@ -335,6 +335,13 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         if (tid == 0) {
             if (a.loss) *a.loss = (float)acc;
             *p.counter = 0u;
+            if (a.xchg && a.loss) {  // multi-GPU loss exchange, as in lattice::finish_loss
+                LossExchange* xchg = a.xchg;
+                const unsigned seq = ++xchg->seq;
+                const unsigned long long entry = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint((float)acc);
+                const size_t slot = (size_t)(seq % (unsigned)kLossRing) * kLossMaxWorld + (size_t)xchg->rank;
+                for (int r = 0; r < xchg->world; ++r) atomicExch_system(xchg->peers[r] + slot, entry);
+            }
         }
     }
 }
@@ -348,7 +355,8 @@ size_t tone_fb_workspace_bytes(int B, int max_t, int max_u, int K) {
     return n + tone_bf_workspace_bytes(B, max_t, max_u, K);
 }
 
-void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream) {
+void launch_tone_forward_backward(const ToneFbArgs& a_in, cudaStream_t stream) {
+    ToneFbArgs a = a_in;
     if (a.batch_size <= 0) {
         if (a.loss) SSNT_CUDA(cudaMemsetAsync(a.loss, 0, sizeof(float), stream));
         return;
@@ -367,13 +375,14 @@ void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream) {
     // Block-float split-role kernel first (tone_bf.cu); the log-domain kernel then redoes only what it flagged.
     const unsigned* only = nullptr;
     bool use_bf = tone_bf_supported(a) && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0;
-    if (const char* e = std::getenv("SSNT_TONE_BF")) use_bf = use_bf && std::atoi(e) != 0;  // tuning / test aid
-    if (use_bf) only = launch_tone_bf(a, (char*)ws + log_bytes, next_done_counter(), stream);
+    if (const char* e = std::getenv("SSNT_TONE_BF")) use_bf = use_bf && std::atoi(e) != 0;  // test aid (both kernels are pinned to the same vectors)
+    if (use_bf) only = launch_tone_bf(a, (char*)ws + log_bytes, done_counter_for(ws), stream);
+    a.xchg = loss_exchange_device();  // only this kernel's reduction is exchanged (the block-float kernel's is provisional)
     ToneParams p;
     p.a = a;
     p.scratch = (float*)ws;
     p.offs = (float*)ws + (size_t)a.batch_size * a.max_t * a.max_u * a.tone_class_size;
-    p.counter = next_done_counter();
+    p.counter = done_counter_for(ws);  // (the block-float kernel above hands it back zeroed before this one starts)
     p.only = only;
     p.fallbacks = device_fallback_counter();
     int threads = ((a.max_u + 31) / 32) * 32;

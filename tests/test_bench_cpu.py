@@ -37,8 +37,27 @@ def test_synthetic_inputs_are_keyed_by_global_index():
     assert np.array_equal(a[2:], b)
 
 
-def test_no_collective_inside_time_bounded_loops():
+def test_no_time_bounded_loop_in_the_gpu_arm():
+    """Every forward_backward call advances the loss exchange's call counter, which must stay in step across
+    ranks: the GPU arm may not contain a loop whose trip count depends on the wall clock."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    for m in re.finditer(r"while time\\.perf_counter\\(\\) < t_end:\\n((?:\\s{16,}.*\\n)+)", src):
-        body = m.group(1)
-        assert "all_reduce" not in body and "step(" not in body and "barrier" not in body, body
+    gpu_arm = src[src.index("def run_b200"):src.index("def main")]
+    assert "while time.perf_counter()" not in gpu_arm
+
+
+def test_graph_length_tiles_any_step_count():
+    sys.path.insert(0, ROOT)
+    from bench import graph_len
+    for steps in (1, 2, 7, 20, 23, 200):
+        g = graph_len(steps)
+        assert 1 <= g <= 10 and steps % g == 0
+    assert graph_len(20) == 10 and graph_len(200) == 10 and graph_len(23) == 1
+
+
+def test_reference_arm_times_the_global_batch():
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                        "--gpus", "2", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 2 and line["config"]["n_batches"] == 2

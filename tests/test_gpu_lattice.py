@@ -438,3 +438,45 @@ def test_device_pointer_call_is_capturable_in_a_cuda_graph(product, oracle_mod):
     for a, b in zip(eager, out):
         assert torch.equal(a, b)
     _check(out, want)
+
+
+# ---- host-pointer calls on ordinary (pageable) numpy arrays, and the loss exchange ------------------------------
+def test_host_pointer_call_on_pageable_arrays_config2(product, oracle_mod):
+    """What the reference's DEVICE_CPU ops hand over (ssnt_tts_v2_beam_search_decode_op.cc:146-177): plain np.empty /
+    np.array buffers, not pinned.  The library page-locks them in place for the call; results must not depend on it."""
+    le, ls = make_inputs(32, 800, 128, seed=99)
+    le, ls = np.array(le, copy=True), np.array(ls, copy=True)
+    want = oracle_mod.forward_backward(le, ls)
+    out = (np.empty(32, np.float32), np.empty(1, np.float32), np.empty((32, 800, 128), np.float32),
+           np.empty((32, 800, 128), np.float32))
+    got = product.forward_backward(le, ls, out=out)
+    _check(got, want)
+    # an unaligned, odd-sized view (page-rounding of the registered range must not matter)
+    le2, ls2 = np.array(le[1:8, :301], copy=True), np.array(ls[1:8, :301], copy=True)
+    want2 = oracle_mod.forward_backward(le2, ls2)
+    _check(product.forward_backward(le2, ls2), want2)
+
+
+def test_loss_exchange_single_rank(product, oracle_mod):
+    """World size 1: the kernel that reduces the loss stores it into this rank's own slot buffer; the all-reduce
+    kernel returns it bit for bit, also when the call is replayed from a CUDA graph."""
+    import ctypes
+    import torch
+    L = product.lib()
+    buf = (ctypes.c_ubyte * 64)()
+    L.ssnt_tts_loss_exchange_export(1, buf)
+    L.ssnt_tts_loss_exchange_connect(0, 1, buf)
+    try:
+        le, ls = make_inputs(5, 96, 64, seed=3)
+        ll, loss, ge, gs = product.forward_backward(_dev(le), _dev(ls))
+        red = product.loss_allreduce()
+        torch.cuda.synchronize()
+        assert torch.equal(red, loss)
+        # tone lattice: the log-domain kernel's reduction is the one that is exchanged
+        le4, ls4, lt4 = make_inputs(3, 40, 32, seed=4, K=4)
+        out = product.tone_latent_forward_backward(_dev(le4), _dev(ls4), _dev(lt4))
+        red = product.loss_allreduce()
+        torch.cuda.synchronize()
+        assert torch.equal(red, out[1])
+    finally:
+        product.disconnect_loss_exchange()
