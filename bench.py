@@ -331,10 +331,13 @@ class Lattice:
             self.graphs[(first + j) % len(self.graphs)].replay()
         return (((first + r - 1) % len(self.graphs)) + 1) * self.group - 1   # index of the last step's set
 
-    def time_steps(self, n, tail=None):
-        """Device time of n steps in ms (CUDA events on torch's current stream); `tail` runs inside the timed region."""
+    def time_steps(self, n, tail=None, head=None):
+        """Device time of n steps in ms (CUDA events on torch's current stream); `tail` runs inside the timed region,
+        `head` is enqueued just before it starts."""
         import torch
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if head:
+            head()
         ev0.record()
         last = self.replay_steps(n)
         extra = tail() if tail else None
@@ -390,10 +393,18 @@ def measure_lattice(P, dev, name, B, steps, warmup, world, rank, fb_kernel=-1, u
         lat.capture(g)
     red = torch.zeros(1, device=dev)
     tail = (lambda: P.loss_allreduce(red)) if exchange else None
+    head = None
+    if exchange:
+        # device-side rendezvous on top of the host barrier: one more graph of steps, then the kernel that waits for
+        # every rank's loss entry — all ranks' streams pass this point within microseconds of each other, so the
+        # timed region (a few hundred microseconds at --steps 20) does not start with the host barrier's exit skew
+        def head():
+            lat.replay_steps(g if use_graph else 1)
+            P.loss_allreduce(red)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms, last, _ = lat.time_steps(steps, tail)
+    ms, last, _ = lat.time_steps(steps, tail, head)
     local_loss = float(lat.loss_all[last].item())
     out = {"ms": ms, "kind": kind, "cells": lat.cells, "nsets": lat.nsets, "set_bytes": lat.set_bytes, "graph_len": g,
            "ngraphs": len(lat.graphs), "local_loss": local_loss, "K": K, "T": T, "U": U, "B": B,
@@ -533,6 +544,8 @@ def run_b200(args):
     P = load_product()
     P.lib()
     if world > 1:
+        # the ranks share the host's cores: split them between the ranks' copy threads (host-pointer calls)
+        os.environ.setdefault("SSNT_COPY_THREADS", str(max(2, min(12, (os.cpu_count() or 8) // world - 1))))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         host_group = dist.new_group(backend="gloo")
@@ -610,8 +623,11 @@ def run_b200(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": 1e3 * e_dt / e2e_steps, "loss_check": e_loss,
                 "pinned_host_memory": {"value": cells_total * e2e_steps / p_dt, "ms_per_step": 1e3 * p_dt / e2e_steps},
-                "note": "host-pointer C-ABI call on ordinary numpy arrays: the library page-locks the caller's buffers in place "
-                        "for the call (cudaHostRegister), copies by DMA in four chunks overlapped with the kernels, unregisters"},
+                "note": "host-pointer C-ABI call on ordinary numpy arrays: the library stages them chunk by chunk through its own "
+                        "page-locked buffers (host-side copies on its copy threads, streaming stores) overlapped with the DMA "
+                        "and the kernels of the neighbouring chunks; caller-pinned buffers are used in place",
+                "copy_threads": int(os.environ.get("SSNT_COPY_THREADS", "0")) or min(12, max(1, (os.cpu_count() or 2) // 2)),
+                "host_cores": os.cpu_count()},
         "gpu_launches": steps * launches_per_step(m["kind"], K),
         "clocks": clk.summary(),
     }

@@ -10,9 +10,14 @@
  * Memory spaces.  Every pointer argument of one call must live in the same memory space:
  *   - device pointers (cudaMalloc / framework GPU tensors): the call only enqueues kernels on
  *     the stream set with ssnt_tts_set_stream() and returns; nothing is copied.
- *   - host pointers (what the reference's DEVICE_CPU ops pass today): inputs are staged to the
+ *   - host pointers (what the reference's DEVICE_CPU ops pass today): inputs are copied to the
  *     GPU, the same kernels run, outputs are copied back and the call returns when the host
- *     buffers are complete.  There is no CPU implementation behind this header.
+ *     buffers are complete.  There is no CPU implementation behind this header.  The lattice
+ *     calls cut the batch into chunks and overlap upload, kernels and download; ordinary
+ *     (pageable) caller buffers go through the library's own page-locked staging buffers, the
+ *     host-side copies spread over a few library threads (SSNT_COPY_THREADS, default
+ *     min(12, cores/2) with the caller's); buffers the caller page-locked are used in place.
+ *     The small decoding calls issue plain cudaMemcpyAsync on the caller's pointers.
  * The space is detected from the first pointer argument (cudaPointerGetAttributes) unless
  * ssnt_tts_set_memory_space() pins it.
  *
@@ -156,6 +161,9 @@ unsigned ssnt_tts_fb_fallback_count(void);
  * cycle counters (total, and cycles blocked on each hand-off barrier); NULL switches it off. */
 void ssnt_tts_debug_set_fb_stats(void *dev_buffer);
 const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
+/* The host-to-host copy the host-pointer lattice calls stage pageable buffers with (spread over the library's copy
+ * threads; SSNT_COPY_THREADS sets their number, the calling thread included).  Returns the thread count.  Test aid. */
+int ssnt_tts_debug_host_copy(void *dst, const void *src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------
  * Block 4 — multi-GPU loss exchange (no counterpart in the reference, which is single-process).

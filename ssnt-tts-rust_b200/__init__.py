@@ -50,6 +50,7 @@ C_SYMBOLS = (
     "ssnt_tts_fb_fallback_count",
     "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
+    "ssnt_tts_debug_host_copy",
     "ssnt_tts_loss_exchange_export",
     "ssnt_tts_loss_exchange_connect",
     "ssnt_tts_loss_exchange_disconnect",

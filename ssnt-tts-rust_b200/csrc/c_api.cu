@@ -68,55 +68,100 @@ private:
     std::vector<Out> outs_;
 };
 
-// Streams used to overlap H2D / kernel / D2H of batch chunks in the host-pointer lattice call: one
-// stream per copy direction (each keeps its DMA engine busy back to back) and a few compute streams
-// (the kernels of small chunks are latency-bound and overlap each other).
-constexpr int kMaxChunks = 8;
+// ---- host-pointer lattice calls: chunked staging pipeline -----------------------------------------------------
+// The batch is cut into chunks; each chunk runs H2D, kernels, D2H in order on its own stream, so chunk c+1 uploads
+// while chunk c computes and chunk c-1 downloads.  Host buffers of the reference's DEVICE_CPU callers are ordinary
+// pageable allocations (ssnt-tts-tensorflow/src/ssnt_tts_v2_beam_search_decode_op.cc:146-177 allocate_output): those
+// are staged through the thread's page-locked scratch, the host-side copies spread over the library's copy threads
+// (host_copy.cu) and overlapped with the DMA of the neighbouring chunks.  Buffers the caller page-locked itself are
+// handed to the DMA engines directly.  A call larger than kStageBytes is processed in several passes so that neither
+// the page-locked nor the device scratch grows with the batch.
+constexpr int kMaxChunks = 16;
 constexpr int kComputeStreams = 8;
+constexpr size_t kStageBytes = (size_t)1 << 30;  // host bytes (inputs + outputs) of one pass
 struct AuxStreams {
-    cudaStream_t h2d = nullptr, d2h = nullptr, k[kComputeStreams] = {};
-    cudaEvent_t start = nullptr, in_done[kMaxChunks] = {}, k_done[kMaxChunks] = {};
+    cudaStream_t k[kComputeStreams] = {};
+    cudaEvent_t start = nullptr, done[kMaxChunks] = {};
     void init() {
-        if (h2d) return;
-        SSNT_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
-        SSNT_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+        if (start) return;
         for (int i = 0; i < kComputeStreams; ++i) SSNT_CUDA(cudaStreamCreateWithFlags(&k[i], cudaStreamNonBlocking));
-        for (int i = 0; i < kMaxChunks; ++i) {
-            SSNT_CUDA(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
-            SSNT_CUDA(cudaEventCreateWithFlags(&k_done[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < kMaxChunks; ++i) SSNT_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         SSNT_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
     }
 };
-thread_local AuxStreams tls_aux;
+thread_local AuxStreams tls_aux[64];  // per device (a host thread may drive several GPUs)
 
-// Host buffers of the reference's DEVICE_CPU callers are ordinary pageable allocations
-// (ssnt-tts-tensorflow/src/ssnt_tts_v2_beam_search_decode_op.cc:146-177 allocate_output).  A cudaMemcpyAsync on
-// pageable memory goes through the driver's bounce buffer and does not overlap with anything, so the lattice calls
-// page-lock the caller's large buffers IN PLACE for the duration of the call (cudaHostRegister; nothing is cached
-// across calls — a cached registration would dangle once the caller frees the buffer) and copy by DMA.
-// SSNT_HOST_REGISTER=0 switches this off (plain copies); buffers that are already pinned, are small, or cannot be
-// registered take the plain path.
-class HostPin {
-public:
-    ~HostPin() {
-        for (void* p : pinned_) cudaHostUnregister(p);
-        cudaGetLastError();
-    }
-    void add(const void* host, size_t bytes) {
-        static const bool enabled = [] { const char* e = std::getenv("SSNT_HOST_REGISTER"); return !e || std::atoi(e) != 0; }();
-        if (!enabled || !host || bytes < ((size_t)1 << 20) || is_pinned_host_pointer(host)) return;
-        // whole pages: round the range outwards (registering a neighbour's page as well is harmless)
-        const uintptr_t lo = reinterpret_cast<uintptr_t>(host) & ~(uintptr_t)4095;
-        const uintptr_t hi = (reinterpret_cast<uintptr_t>(host) + bytes + 4095) & ~(uintptr_t)4095;
-        if (cudaHostRegister(reinterpret_cast<void*>(lo), hi - lo, cudaHostRegisterDefault) == cudaSuccess)
-            pinned_.push_back(reinterpret_cast<void*>(lo));
-        else
-            cudaGetLastError();  // e.g. overlaps a range somebody else registered: plain copies still work
-    }
-private:
-    std::vector<void*> pinned_;
+// One host array of a lattice call, cut along the batch axis.
+struct HostArray {
+    const void* host_in;  // inputs
+    void* host_out;       // outputs
+    size_t per_b;         // bytes per utterance
+    int slot;             // scratch slot (device and page-locked)
+    char* dev = nullptr;
+    char* stage = nullptr;  // page-locked staging copy, or the caller's own buffer if that is page-locked
+    bool direct = false;
 };
+
+// launch(b0, nb, chunk, stream): enqueues the kernels of utterances [b0, b0 + nb) (device arrays via .dev).
+template <class Launch>
+void staged_lattice_pass(std::vector<HostArray>& ins, std::vector<HostArray>& outs, int B, int nchunks, Launch&& launch) {
+    HostCopier copier;
+    for (auto* v : {&ins, &outs})
+        for (HostArray& a : *v) {
+            const void* user = a.host_in ? a.host_in : a.host_out;
+            a.dev = (char*)device_scratch(a.slot, a.per_b * B + 16);
+            a.direct = is_pinned_host_pointer(user);
+            a.stage = a.direct ? (char*)const_cast<void*>(user) : (char*)pinned_scratch(a.slot, a.per_b * B + 16);
+        }
+    AuxStreams& aux = tls_aux[device_ordinal()];
+    aux.init();
+    SSNT_CUDA(cudaEventRecord(aux.start, current_stream()));
+    const int per = (B + nchunks - 1) / nchunks;
+    int issued = 0, drained = 0;
+    auto drain = [&](int c) {  // chunk c has landed in the staging buffers: hand it to the caller
+        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
+        for (HostArray& a : outs)
+            if (!a.direct) copier.copy((char*)a.host_out + (size_t)b0 * a.per_b, a.stage + (size_t)b0 * a.per_b, (size_t)nb * a.per_b);
+    };
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
+        if (nb <= 0) break;
+        cudaStream_t s = aux.k[c % kComputeStreams];
+        if (c < kComputeStreams) SSNT_CUDA(cudaStreamWaitEvent(s, aux.start, 0));
+        for (HostArray& a : ins) {
+            const size_t o = (size_t)b0 * a.per_b, n = (size_t)nb * a.per_b;
+            if (!a.direct) copier.copy(a.stage + o, (const char*)a.host_in + o, n);
+            SSNT_CUDA(cudaMemcpyAsync(a.dev + o, a.stage + o, n, cudaMemcpyHostToDevice, s));
+        }
+        launch(b0, nb, c, s);
+        for (HostArray& a : outs) {
+            const size_t o = (size_t)b0 * a.per_b, n = (size_t)nb * a.per_b;
+            SSNT_CUDA(cudaMemcpyAsync(a.stage + o, a.dev + o, n, cudaMemcpyDeviceToHost, s));
+        }
+        SSNT_CUDA(cudaEventRecord(aux.done[c], s));
+        issued = c + 1;
+        // whatever has completed meanwhile goes out now, while the later chunks are in flight
+        while (drained < issued - 1 && cudaEventQuery(aux.done[drained]) == cudaSuccess) drain(drained++);
+    }
+    for (; drained < issued; ++drained) {
+        SSNT_CUDA(cudaEventSynchronize(aux.done[drained]));
+        drain(drained);
+    }
+    cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+}
+
+int lattice_chunks(int B, size_t in_bytes) {
+    // measured at cfg2 (26 MB in, 26 MB out) — see DESIGN.md §4.4; small calls are not worth cutting
+    int n = 1;
+    // cfg2, pageable, 12 copy threads: 2 chunks 1.24 ms, 3: 1.12, 4: 1.11, 5: 1.07-1.18, 6: 1.13-1.21, 8: 1.20-1.26, 10: 1.19-1.25
+    if (B >= 2 && in_bytes >= ((size_t)2 << 20)) n = (int)(in_bytes / ((size_t)6 << 20));
+    n = n < 2 ? (B >= 2 && in_bytes >= ((size_t)2 << 20) ? 2 : 1) : n;
+    n = n > 8 ? 8 : n;
+    static const int env_chunks = [] { const char* e = std::getenv("SSNT_FB_CHUNKS"); return e ? std::atoi(e) : 0; }();  // tuning aid
+    if (env_chunks > 0) n = env_chunks > kMaxChunks ? kMaxChunks : env_chunks;
+    if (n > B) n = B > 0 ? B : 1;
+    return n;
+}
 
 }  // namespace
 }  // namespace ssnt
@@ -300,58 +345,34 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
         launch_forward_backward(a, current_stream());
         return;
     }
-    // Host buffers: split the batch into chunks, one stream per chunk (H2D, kernel, D2H in stream
-    // order).  The copy engines serve the streams in issue order, so chunk c+1 uploads while chunk c
-    // computes and chunk c-1 downloads: the PCIe link is busy in both directions.  Few API calls per
-    // chunk matter as much as the overlap: the host thread's issue time (~5 us per call) is on the
-    // critical path of a ~0.7 ms call, hence no events and one download of the likelihoods at the end.
-    const size_t slab = n2(max_t, max_u);
+    // Host buffers: the chunked staging pipeline above, in passes of at most kStageBytes.
+    const size_t slab = n2(max_t, max_u) * sizeof(float);
     const int B = batch_size > 0 ? batch_size : 0;
-    HostPin pin;  // unregisters when the call returns (every copy has completed by then)
-    pin.add(log_emit, B * slab * sizeof(float));
-    pin.add(log_shift, B * slab * sizeof(float));
-    pin.add(grad_emit, B * slab * sizeof(float));
-    pin.add(grad_shift, B * slab * sizeof(float));
-    float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
-    float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
-    float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
-    float* d_gs = (float*)device_scratch(7, B * slab * sizeof(float) + 16);
-    float* d_ll = (float*)device_scratch(8, (size_t)B * sizeof(float) + 16);
-    int* d_tl = (int*)device_scratch(9, (size_t)B * sizeof(int) + 16);
-    int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
-    int nchunks = 1;
-    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 8 ? 4 : 2;  // measured: 4 chunks 0.82 ms, 6: 0.86, 8: 0.89 (cfg2; PCIe floor ~0.6)
-    static const int env_chunks = [] { const char* e = std::getenv("SSNT_FB_CHUNKS"); return e ? std::atoi(e) : 0; }();  // tuning aid
-    if (env_chunks > 0) {
-        nchunks = env_chunks > kMaxChunks ? kMaxChunks : env_chunks;
-        if (nchunks > B) nchunks = B > 0 ? B : 1;
+    const size_t per_b = 4 * slab + 3 * sizeof(int);
+    const int pass_b = per_b * B <= kStageBytes ? B : (int)(kStageBytes / per_b > 0 ? kStageBytes / per_b : 1);
+    for (int p0 = 0; p0 < B; p0 += pass_b) {
+        const int nb_pass = p0 + pass_b <= B ? pass_b : B - p0;
+        const size_t o = (size_t)p0 * (slab / sizeof(float));
+        std::vector<HostArray> ins = {{log_emit + o, nullptr, slab, 4}, {log_shift + o, nullptr, slab, 5}};
+        if (t_len) ins.push_back({t_len + p0, nullptr, sizeof(int), 9});
+        if (u_len) ins.push_back({u_len + p0, nullptr, sizeof(int), 10});
+        std::vector<HostArray> outs = {{nullptr, grad_emit + o, slab, 6}, {nullptr, grad_shift + o, slab, 7},
+                                       {nullptr, log_likelihood + p0, sizeof(float), 8}};
+        const int nchunks = lattice_chunks(nb_pass, 2 * slab * nb_pass);
+        const int per = (nb_pass + nchunks - 1) / nchunks;
+        const size_t ws_each = (fb_workspace_bytes(per, max_t, max_u) + 255) & ~(size_t)255;
+        char* ws = (char*)device_scratch(0, ws_each * nchunks);
+        const int i_tl = t_len ? 2 : -1, i_ul = u_len ? (t_len ? 3 : 2) : -1;
+        staged_lattice_pass(ins, outs, nb_pass, nchunks, [&](int b0, int nb, int c, cudaStream_t s) {
+            const size_t e = (size_t)b0 * (slab / sizeof(float));
+            FbArgs a{(const float*)ins[0].dev + e, (const float*)ins[1].dev + e,
+                     i_tl >= 0 ? (const int*)ins[i_tl].dev + b0 : nullptr, i_ul >= 0 ? (const int*)ins[i_ul].dev + b0 : nullptr,
+                     nb, max_t, max_u, (float*)outs[2].dev + b0, nullptr, (float*)outs[0].dev + e, (float*)outs[1].dev + e,
+                     ws + (size_t)c * ws_each, ws_each};
+            launch_forward_backward(a, s);
+        });
     }
-    const int per = (B + nchunks - 1) / (nchunks > 0 ? nchunks : 1);
-    const size_t ws_each = fb_workspace_bytes(per, max_t, max_u);
-    char* ws = (char*)device_scratch(0, ws_each * nchunks);
-    tls_aux.init();
-    cudaStream_t main_stream = current_stream();
-    SSNT_CUDA(cudaEventRecord(tls_aux.start, main_stream));
-    int used = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
-        if (nb <= 0) break;
-        cudaStream_t s = tls_aux.k[c % kComputeStreams];
-        if (c < kComputeStreams) SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
-        const size_t o = (size_t)b0 * slab, nbytes = (size_t)nb * slab * sizeof(float);
-        SSNT_CUDA(cudaMemcpyAsync(d_le + o, log_emit + o, nbytes, cudaMemcpyHostToDevice, s));
-        SSNT_CUDA(cudaMemcpyAsync(d_ls + o, log_shift + o, nbytes, cudaMemcpyHostToDevice, s));
-        if (t_len) SSNT_CUDA(cudaMemcpyAsync(d_tl + b0, t_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
-        if (u_len) SSNT_CUDA(cudaMemcpyAsync(d_ul + b0, u_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
-        FbArgs a{d_le + o, d_ls + o, t_len ? d_tl + b0 : nullptr, u_len ? d_ul + b0 : nullptr, nb, max_t,
-                 max_u, d_ll + b0, nullptr, d_ge + o, d_gs + o, ws + (size_t)c * ws_each, ws_each};
-        launch_forward_backward(a, s);
-        SSNT_CUDA(cudaMemcpyAsync(grad_emit + o, d_ge + o, nbytes, cudaMemcpyDeviceToHost, s));
-        SSNT_CUDA(cudaMemcpyAsync(grad_shift + o, d_gs + o, nbytes, cudaMemcpyDeviceToHost, s));
-        used = c + 1;
-    }
-    for (int i = 0; i < kComputeStreams && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.k[i]));
-    if (B > 0) SSNT_CUDA(cudaMemcpy(log_likelihood, d_ll, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost));
+    check_error_flag_or_panic();
     if (loss) {
         // loss = -sum_b ll[b] in batch order, in double (what the kernel's own reduction computes)
         double acc = 0.0;
@@ -376,63 +397,37 @@ void tone_latent_forward_backward(const float* log_emit, const float* log_shift,
         launch_tone_forward_backward(a, current_stream());
         return;
     }
-    // Host buffers: the same chunked H2D / kernel / D2H pipeline as ssnt_tts_forward_backward above.
+    // Host buffers: the same chunked staging pipeline as ssnt_tts_forward_backward above.
     const int K = tone_class_size > 0 ? tone_class_size : 0;
     const int B = batch_size > 0 ? batch_size : 0;
-    const size_t slab = n2(max_t, max_u) * (size_t)K, tslab = n2(max_u, K);
-    HostPin pin;
-    pin.add(log_emit, B * slab * sizeof(float));
-    pin.add(log_shift, B * slab * sizeof(float));
-    pin.add(grad_emit, B * slab * sizeof(float));
-    pin.add(grad_shift, B * slab * sizeof(float));
-    float* d_le = (float*)device_scratch(4, B * slab * sizeof(float) + 16);
-    float* d_ls = (float*)device_scratch(5, B * slab * sizeof(float) + 16);
-    float* d_ge = (float*)device_scratch(6, B * slab * sizeof(float) + 16);
-    float* d_gs = (float*)device_scratch(7, B * slab * sizeof(float) + 16);
-    float* d_ll = (float*)device_scratch(8, (size_t)B * sizeof(float) + 16);
-    int* d_tl = (int*)device_scratch(9, (size_t)B * sizeof(int) + 16);
-    int* d_ul = (int*)device_scratch(10, (size_t)B * sizeof(int) + 16);
-    float* d_lt = (float*)device_scratch(11, B * tslab * sizeof(float) + 16);
-    float* d_gt = (float*)device_scratch(12, B * tslab * sizeof(float) + 16);
-    int nchunks = 1;
-    // measured on config 3 (2 x 105 MB): 2 chunks 3.26 ms, 4: 3.06, 6: 2.81, 8: 3.02 (unchunked 4.04)
-    if (B >= 2 && B * slab * sizeof(float) >= ((size_t)2 << 20)) nchunks = B >= 12 ? 6 : (B >= 8 ? 4 : 2);
-    static const int env_chunks = [] { const char* e = std::getenv("SSNT_FB_CHUNKS"); return e ? std::atoi(e) : 0; }();  // tuning aid
-    if (env_chunks > 0) {
-        nchunks = env_chunks > kMaxChunks ? kMaxChunks : env_chunks;
-        if (nchunks > B) nchunks = B > 0 ? B : 1;
+    const size_t slab = n2(max_t, max_u) * (size_t)K * sizeof(float), tslab = n2(max_u, K) * sizeof(float);
+    const size_t per_b = 4 * slab + 2 * tslab + 3 * sizeof(int);
+    const int pass_b = per_b * B <= kStageBytes ? B : (int)(kStageBytes / per_b > 0 ? kStageBytes / per_b : 1);
+    for (int p0 = 0; p0 < B; p0 += pass_b) {
+        const int nb_pass = p0 + pass_b <= B ? pass_b : B - p0;
+        const size_t o = (size_t)p0 * (slab / sizeof(float)), ot = (size_t)p0 * (tslab / sizeof(float));
+        std::vector<HostArray> ins = {{log_tone + ot, nullptr, tslab, 11}, {log_emit + o, nullptr, slab, 4},
+                                      {log_shift + o, nullptr, slab, 5}};
+        if (t_len) ins.push_back({t_len + p0, nullptr, sizeof(int), 9});
+        if (u_len) ins.push_back({u_len + p0, nullptr, sizeof(int), 10});
+        std::vector<HostArray> outs = {{nullptr, grad_emit + o, slab, 6}, {nullptr, grad_shift + o, slab, 7},
+                                       {nullptr, grad_tone + ot, tslab, 12}, {nullptr, log_likelihood + p0, sizeof(float), 8}};
+        const int nchunks = lattice_chunks(nb_pass, 2 * slab * nb_pass);
+        const int per = (nb_pass + nchunks - 1) / nchunks;
+        // every chunk's workspace starts 256-byte aligned (the block-float kernel needs 16)
+        const size_t ws_each = (tone_fb_workspace_bytes(per, max_t, max_u, K) + 255) & ~(size_t)255;
+        char* ws = (char*)device_scratch(1, ws_each * nchunks);
+        const int i_tl = t_len ? 3 : -1, i_ul = u_len ? (t_len ? 4 : 3) : -1;
+        staged_lattice_pass(ins, outs, nb_pass, nchunks, [&](int b0, int nb, int c, cudaStream_t s) {
+            const size_t e = (size_t)b0 * (slab / sizeof(float)), et = (size_t)b0 * (tslab / sizeof(float));
+            ToneFbArgs a{(const float*)ins[1].dev + e, (const float*)ins[2].dev + e, (const float*)ins[0].dev + et,
+                         i_tl >= 0 ? (const int*)ins[i_tl].dev + b0 : nullptr, i_ul >= 0 ? (const int*)ins[i_ul].dev + b0 : nullptr,
+                         nb, max_t, max_u, tone_class_size, (float*)outs[3].dev + b0, nullptr, (float*)outs[0].dev + e,
+                         (float*)outs[1].dev + e, (float*)outs[2].dev + et, ws + (size_t)c * ws_each, ws_each};
+            launch_tone_forward_backward(a, s);
+        });
     }
-    const int per = (B + nchunks - 1) / nchunks;
-    // every chunk's workspace starts 256-byte aligned (the block-float kernel needs 16)
-    const size_t ws_each = (tone_fb_workspace_bytes(per, max_t, max_u, K) + 255) & ~(size_t)255;
-    char* ws = (char*)device_scratch(1, ws_each * nchunks);
-    tls_aux.init();
-    cudaStream_t main_stream = current_stream();
-    SSNT_CUDA(cudaEventRecord(tls_aux.start, main_stream));
-    int used = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * per, nb = (b0 + per <= B ? per : B - b0);
-        if (nb <= 0) break;
-        cudaStream_t s = tls_aux.k[c % kComputeStreams];
-        SSNT_CUDA(cudaStreamWaitEvent(s, tls_aux.start, 0));
-        const size_t o = (size_t)b0 * slab, nbytes = (size_t)nb * slab * sizeof(float);
-        const size_t ot = (size_t)b0 * tslab, tbytes = (size_t)nb * tslab * sizeof(float);
-        SSNT_CUDA(cudaMemcpyAsync(d_lt + ot, log_tone + ot, tbytes, cudaMemcpyHostToDevice, s));
-        SSNT_CUDA(cudaMemcpyAsync(d_le + o, log_emit + o, nbytes, cudaMemcpyHostToDevice, s));
-        SSNT_CUDA(cudaMemcpyAsync(d_ls + o, log_shift + o, nbytes, cudaMemcpyHostToDevice, s));
-        if (t_len) SSNT_CUDA(cudaMemcpyAsync(d_tl + b0, t_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
-        if (u_len) SSNT_CUDA(cudaMemcpyAsync(d_ul + b0, u_len + b0, nb * sizeof(int), cudaMemcpyHostToDevice, s));
-        ToneFbArgs a{d_le + o, d_ls + o, d_lt + ot, t_len ? d_tl + b0 : nullptr, u_len ? d_ul + b0 : nullptr, nb,
-                     max_t, max_u, tone_class_size, d_ll + b0, nullptr, d_ge + o, d_gs + o, d_gt + ot,
-                     ws + (size_t)c * ws_each, ws_each};
-        launch_tone_forward_backward(a, s);
-        SSNT_CUDA(cudaMemcpyAsync(grad_emit + o, d_ge + o, nbytes, cudaMemcpyDeviceToHost, s));
-        SSNT_CUDA(cudaMemcpyAsync(grad_shift + o, d_gs + o, nbytes, cudaMemcpyDeviceToHost, s));
-        SSNT_CUDA(cudaMemcpyAsync(grad_tone + ot, d_gt + ot, tbytes, cudaMemcpyDeviceToHost, s));
-        used = c + 1;
-    }
-    for (int i = 0; i < kComputeStreams && i < used; ++i) SSNT_CUDA(cudaStreamSynchronize(tls_aux.k[i]));
-    if (B > 0) SSNT_CUDA(cudaMemcpy(log_likelihood, d_ll, (size_t)B * sizeof(float), cudaMemcpyDeviceToHost));
+    check_error_flag_or_panic();
     if (loss) {
         double acc = 0.0;  // loss = -sum_b ll[b] in batch order, in double (as the kernel's own reduction)
         for (int b2 = 0; b2 < B; ++b2) acc -= (double)log_likelihood[b2];
@@ -463,6 +458,12 @@ unsigned ssnt_tts_fb_fallback_count(void) {
     return read_fallback_counter();
 }
 const char* ssnt_tts_backend(void) { return "cuda-sm_100a"; }
+int ssnt_tts_debug_host_copy(void* dst, const void* src, size_t bytes) {
+    NOT_NULL(dst); NOT_NULL(src);
+    HostCopier c;
+    c.copy(dst, src, bytes);
+    return host_copy_threads();
+}
 
 // ---- multi-GPU loss exchange (batch-sharded training) ---------------------------------------------
 void ssnt_tts_loss_exchange_export(int world_size, unsigned char* handle_out) {

@@ -152,8 +152,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // Deterministic loss = -sum_b ll[b]: the last CTA to finish adds the B values in index order.  With a connected
-// loss exchange (multi-GPU, runtime.cu) the same thread then stores {loss, call number} into every rank's slot buffer
-// over NVLink — one 64-bit store per peer, nothing else is launched for the all-reduce.
+// loss exchange (multi-GPU, runtime.cu) the same warp then stores {loss, call number} into every rank's slot buffer
+// over NVLink — lane r one posted 64-bit store to rank r, nothing else is launched for the all-reduce.
 static __device__ void finish_loss(const float* ll, float* loss, int B, unsigned* counter, int lane, int nthreads,
                                    LossExchange* xchg = nullptr) {
     __shared__ unsigned s_last;
@@ -170,13 +170,8 @@ static __device__ void finish_loss(const float* ll, float* loss, int B, unsigned
         if (lane == 0) {
             if (loss) *loss = (float)acc;
             *counter = 0u;  // hand the counter back zeroed
-            if (xchg && loss) {
-                const unsigned seq = ++xchg->seq;
-                const unsigned long long entry = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint((float)acc);
-                const size_t slot = (size_t)(seq % (unsigned)kLossRing) * kLossMaxWorld + (size_t)xchg->rank;
-                for (int r = 0; r < xchg->world; ++r) atomicExch_system(xchg->peers[r] + slot, entry);
-            }
         }
+        if (xchg && loss) loss_exchange_publish(xchg, (float)acc, lane);
     }
     (void)nthreads;
 }

@@ -63,11 +63,37 @@ struct LossExchange {
     unsigned seq;                                 // calls completed so far (device side; advances under graph replay)
     unsigned long long* peers[kLossMaxWorld];     // every rank's slot buffer [kLossRing][kLossMaxWorld] of {loss bits, seq}
 };
+#ifdef __CUDACC__
+// Called by the 32 lanes of the warp that has just reduced a call's loss (every lane holds `loss`): lane r posts
+// {loss bits, call number} into rank r's slot buffer with one plain 64-bit store over NVLink.  Posted stores: the
+// warp does not wait for a round trip; the reader polls for the call number (loss_allreduce_kernel).
+__device__ __forceinline__ void loss_exchange_publish(LossExchange* x, float loss, int lane) {
+    unsigned seq = 0;
+    if (lane == 0) seq = ++x->seq;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    if (lane < x->world) {
+        const unsigned long long entry = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(loss);
+        unsigned long long* dst = x->peers[lane] + (size_t)(seq % (unsigned)kLossRing) * kLossMaxWorld + (size_t)x->rank;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(entry) : "memory");
+    }
+}
+#endif
 void loss_exchange_export(int world, unsigned char handle_out[64]);
 void loss_exchange_connect(int rank, int world, const unsigned char* handles);
 void loss_exchange_disconnect();
 LossExchange* loss_exchange_device();      // null until connected
 void launch_loss_allreduce(float* out_device, cudaStream_t stream);
+
+// Host-to-host copies spread over the library's copy threads for the duration of one call (host_copy.cu).
+class HostCopier {
+public:
+    HostCopier();
+    ~HostCopier();
+    void copy(void* dst, const void* src, size_t bytes);
+private:
+    bool pooled_;
+};
+int host_copy_threads();
 
 // Grow-only per-thread device scratch (workspace the caller did not provide, staging of host
 // buffers).  Slots are independent so one call can hold several live buffers.

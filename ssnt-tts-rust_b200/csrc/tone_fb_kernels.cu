@@ -335,14 +335,8 @@ __global__ void tone_fb_kernel(const ToneParams p) {
         if (tid == 0) {
             if (a.loss) *a.loss = (float)acc;
             *p.counter = 0u;
-            if (a.xchg && a.loss) {  // multi-GPU loss exchange, as in lattice::finish_loss
-                LossExchange* xchg = a.xchg;
-                const unsigned seq = ++xchg->seq;
-                const unsigned long long entry = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint((float)acc);
-                const size_t slot = (size_t)(seq % (unsigned)kLossRing) * kLossMaxWorld + (size_t)xchg->rank;
-                for (int r = 0; r < xchg->world; ++r) atomicExch_system(xchg->peers[r] + slot, entry);
-            }
         }
+        if (a.xchg && a.loss) loss_exchange_publish(a.xchg, (float)acc, tid);  // multi-GPU, as in lattice::finish_loss
     }
 }
 

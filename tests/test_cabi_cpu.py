@@ -66,3 +66,40 @@ def test_shard_range_partitions_the_batch(product):
             assert all(spans[i][1] == spans[i + 1][0] for i in range(N - 1))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_copy_pool_copies_exactly(product):
+    """The copy threads behind the host-pointer lattice calls (csrc/host_copy.cu): every byte arrives, for sizes
+    around the piece size, unaligned ends, and from several caller threads at once (a busy pool means the caller
+    copies by itself)."""
+    import ctypes
+    import threading
+
+    import numpy as np
+    lib = product.lib()
+    lib.ssnt_tts_debug_host_copy.restype = ctypes.c_int
+    lib.ssnt_tts_debug_host_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, 9_000_001, dtype=np.uint8)
+
+    def one(n, off):
+        dst = np.zeros(n + 64, np.uint8)
+        nt = lib.ssnt_tts_debug_host_copy(dst.ctypes.data + 7, src.ctypes.data + off, n)
+        assert nt >= 1
+        assert np.array_equal(dst[7:7 + n], src[off:off + n])
+        assert not dst[:7].any() and not dst[7 + n:].any()
+
+    for n in (1, 4095, 262144, 262145, 524288, 3_000_000, 9_000_000):
+        one(n, 1)
+    errs = []
+
+    def worker(k):
+        try:
+            for i in range(20):
+                one(1_000_000 + 4099 * k + i, k)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
