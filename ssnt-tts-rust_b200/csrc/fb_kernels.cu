@@ -15,6 +15,7 @@
 //            domain with one integer offset per token.
 #include "fb_split.cuh"
 #include "fb_tp.cuh"
+#include "fb_tp4.cuh"
 
 namespace ssnt {
 namespace {
@@ -429,6 +430,40 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     }
 }
 
+// Register-sweep time-parallel path (kind 8): group operators, boundary vectors, group interiors.
+template <int CPL>
+void launch_tp4(const TpParams& p, cudaStream_t stream) {
+    const FbArgs& a = p.a;
+    const size_t chunk_smem = 128 + (size_t)2 * kTp4Rows * a.max_u * sizeof(float);
+    const size_t ring_smem = 128 + (size_t)Tp4Dims<CPL>::NS * Tp4Dims<CPL>::stage_floats * sizeof(float);
+    static bool configured_[64] = {};  // per device
+    bool& configured = configured_[device_ordinal()];
+    if (!configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(tp4_sweep_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        configured = true;
+    }
+    const unsigned tasks = (unsigned)a.batch_size * (unsigned)((a.max_t + kTp4Rows - 1) / kTp4Rows);
+    tp4_build_kernel<CPL><<<tasks, 32, chunk_smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = stream;
+    cfg.attrs = pdl;
+    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 7; }();  // tuning aid: 1 sweep, 2 fill, 4 re-run
+    cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
+    cfg.gridDim = dim3((unsigned)a.batch_size * 2u);
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = ring_smem;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp4_sweep_kernel<CPL>, p));
+    cfg.numAttrs = (pdl_mask & 2) ? 1 : 0;
+    cfg.gridDim = dim3(tasks);
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = chunk_smem;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp4_fill_kernel<CPL>, p));
+}
+
 }  // namespace
 
 // Time-parallel path (kind 6): region 0 holds the chunk operators Q [B][C][L+1][UP] and is re-used as the scratch
@@ -448,6 +483,28 @@ static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
     const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
     l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
     l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
+    l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
+              (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
+    return true;
+}
+
+// Register-sweep time-parallel path (kind 8): region 0 holds the group operators Q [B][NG][5][UP+4] (re-used as the
+// scratch rows of the log-domain re-run), then the boundary vectors A, Bv [B][NG+1][UP+32], the likelihood estimates
+// and the status words.
+struct Tp4Layout {
+    int CPL, UP, NG, SU;
+    size_t region0, vec, total;
+};
+static bool tp4_layout(int B, int max_t, int max_u, Tp4Layout& l) {
+    if (max_u % 4 != 0 || max_u > 256 || max_u <= 0 || max_t <= 0 || B <= 0) return false;
+    l.CPL = max_u <= 128 ? 4 : 8;
+    l.UP = 32 * l.CPL;
+    l.NG = (max_t + kTp4L - 1) / kTp4L;
+    l.SU = max_u + 32;
+    const size_t q = (size_t)B * l.NG * (kTp4L + 1) * (l.UP + 4) * sizeof(float);
+    const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
+    l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
+    l.vec = (((size_t)B * (l.NG + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
     l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
               (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
     return true;
@@ -475,6 +532,8 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     n = n > split_bytes ? n : split_bytes;
     TpLayout tl;
     if (tp_layout(B, max_t, max_u, tl)) n = n > tl.total ? n : tl.total;
+    Tp4Layout t4;
+    if (tp4_layout(B, max_t, max_u, t4)) n = n > t4.total ? n : t4.total;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -564,6 +623,46 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         static const bool pdl4 = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? (std::atoi(e) & 4) != 0 : true; }();
         if (tl.CPL == 2) launch_warp<2>(lp, smem, stream, pdl4);
         else if (tl.CPL == 4) launch_warp<4>(lp, smem, stream, pdl4);
+        else launch_warp<8>(lp, smem, stream, pdl4);
+        return;
+    }
+    if (kind == 8 || kind == 9) {
+        Tp4Layout tl;
+        SSNT_ASSERT(bf_ok && tp4_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: register-sweep kernels forced on an unsupported shape");
+        tls_last_kind = kind;
+        TpParams p;
+        p.a = a;
+        char* base = (char*)ws;
+        p.Q = (float*)base;
+        p.A = (float*)(base + tl.region0);
+        p.Bv = (float*)(base + tl.region0 + tl.vec);
+        p.zlg = (float*)(base + tl.region0 + 2 * tl.vec);
+        p.status = (unsigned*)(base + tl.region0 + 2 * tl.vec + (((size_t)a.batch_size * 4 * sizeof(float) + 255) & ~(size_t)255));
+        p.C = tl.NG;
+        p.UP = tl.UP;
+        p.NS = 0;
+        p.G = tl.CPL;
+        p.debug = 0;
+        p.force_fallback = kind == 9 ? 1 : 0;  // kind 9: run the kernels but force the log-domain re-run
+        if (tl.CPL == 4) launch_tp4<4>(p, stream);
+        else launch_tp4<8>(p, stream);
+        // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
+        LogParams lp;
+        lp.a = a;
+        lp.scratch = (float*)ws;
+        lp.SU = tl.SU;
+        lp.counter = counter;
+        lp.only = p.status;
+        lp.fallbacks = device_fallback_counter();
+        const size_t stage_bytes = (size_t)kG * (2 * a.max_u + lp.SU) * sizeof(float);
+        const bool latency_mode = (size_t)a.batch_size * 2 <= (size_t)sm_count();
+        int LNS = (int)((latency_mode ? 192 * 1024 : 52 * 1024) / stage_bytes);
+        lp.NS = LNS < 2 ? 2 : (LNS > 8 ? 8 : LNS);
+        const size_t smem = 128 + (size_t)lp.NS * stage_bytes;
+        static const bool pdl4 = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? (std::atoi(e) & 4) != 0 : true; }();
+        const int lcpl = a.max_u <= 64 ? 2 : (a.max_u <= 128 ? 4 : 8);
+        if (lcpl == 2) launch_warp<2>(lp, smem, stream, pdl4);
+        else if (lcpl == 4) launch_warp<4>(lp, smem, stream, pdl4);
         else launch_warp<8>(lp, smem, stream, pdl4);
         return;
     }

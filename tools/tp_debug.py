@@ -6,7 +6,7 @@ from lattice_util import make_inputs
 B, T, U = [int(x) for x in sys.argv[1:4]]
 P = load_product(); P.lib()
 le, ls = make_inputs(B, T, U, seed=1)
-P.set_fb_kernel(6)
+P.set_fb_kernel(int(sys.argv[4]) if len(sys.argv) > 4 else 6)
 d = lambda a: torch.as_tensor(a, device="cuda")
 print("calling", flush=True)
 out = P.forward_backward(d(le), d(ls))
