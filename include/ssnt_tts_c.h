@@ -166,6 +166,37 @@ const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
 int ssnt_tts_debug_host_copy(void *dst, const void *src, size_t bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * Block 2b — whole-loop decoding (no counterpart in the reference's ABI).
+ * The reference decodes with one call per output step (ssnt-tts-tensorflow/ssnt_tts_tensorflow/__init__.py:33-73 is
+ * meant for a tf.while_loop), then back-traces (src/v2_util.rs:6-36) and upsamples (src/v2_util.rs:39-66).  When the
+ * per-step scores are known up front, h[B, steps, W, classes], one launch does all of it and the results equal the
+ * per-step calls bit for bit:
+ *   every step s = 0..steps-1: ssnt_tts_v2_beam_search_decode (src/v2.rs:221-339) on h[:, s] and the running state;
+ *     prediction_history, beam_branch_history [B, steps, W] record each step's prediction and beam_branch
+ *   log_probs / final_* [B, W]: the state after the last step
+ *   ordered_beam_branch [B, W, steps] = ssnt_order_beam_branch(final_branch = 0..W-1, beam_branch_history)
+ *   duration [B, W, steps] = duration_table[prediction_history gathered along ordered_beam_branch]
+ *   upsampled_source_indexes [B, W, max_u] (may be NULL; caller pre-filled) =
+ *     ssnt_upsample_source_indexes(duration, output_length = final_total_duration)
+ * The initial state pointers (log_prob_history, is_finished, total_duration, t, u; [B, W]) may be NULL = zeros / false.
+ * tone_latent_decode_loop is the same over tone_latent_beam_search_decode (src/tone_latent.rs:144-234);
+ * ordered_tone [B, W, steps] = prediction_history gathered along ordered_beam_branch.
+ * ---------------------------------------------------------------------------------------- */
+void ssnt_tts_v2_decode_loop(const float *h, const int *duration_table, const int *input_length,
+                             const int *output_length, const float *log_prob_history,
+                             const bool *is_finished, const int *total_duration, const int *t, const int *u,
+                             int batch_size, int steps, int beam_width, int duration_class_size,
+                             int zero_duration_id, bool allow_skip, bool test_mode, int max_u,
+                             int *prediction_history, int *beam_branch_history, float *log_probs, int *final_t,
+                             int *final_u, bool *final_is_finished, int *final_total_duration,
+                             int *ordered_beam_branch, int *duration, int *upsampled_source_indexes);
+void tone_latent_decode_loop(const float *h, const int *input_length, const float *log_prob_history,
+                             const bool *is_finished, const int *t, const int *u, int batch_size, int steps,
+                             int beam_width, int tone_class_size, int empty_tone_id, int *prediction_history,
+                             int *beam_branch_history, float *log_probs, int *final_t, int *final_u,
+                             bool *final_is_finished, int *ordered_beam_branch, int *ordered_tone);
+
+/* ------------------------------------------------------------------------------------------
  * Block 4 — multi-GPU loss exchange (no counterpart in the reference, which is single-process).
  * Utterances are independent, so N GPUs each take a batch shard (the reference's par_chunks over
  * the batch, src/v2.rs:227); the one value that crosses GPUs is the scalar loss.  Once connected,

@@ -51,6 +51,8 @@ C_SYMBOLS = (
     "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
     "ssnt_tts_debug_host_copy",
+    "ssnt_tts_v2_decode_loop",
+    "tone_latent_decode_loop",
     "ssnt_tts_loss_exchange_export",
     "ssnt_tts_loss_exchange_connect",
     "ssnt_tts_loss_exchange_disconnect",
@@ -289,6 +291,63 @@ def levenshtein_edit_distance(a, b, a_lengths, b_lengths):
     out, p_out = c.out((B,), "i32")
     lib().tone_latent_levenshtein_edit_distance(*args, c_int(B), c_int(L), p_out)
     return out
+
+
+# ---- whole-loop decoding (new) ---------------------------------------------------
+def ssnt_tts_v2_decode_loop(h, duration_table, input_length, output_length, beam_width, duration_class_size,
+                            zero_duration_id, allow_skip, test_mode, max_u, out_of_range_source_index,
+                            log_prob_history=None, is_finished=None, total_duration=None, t=None, u=None):
+    """Every v2 step of `ssnt_tts_v2_beam_search_decode` (`__init__.py:33-73`) for h[B, steps, W, D] in one launch,
+    then `order_beam_branch` (final_branch = 0..W-1), the durations along each branch and
+    `upsample_source_indexes` with output_length = the beams' final total durations (`__init__.py:76-96`).
+    As in the per-step wrapper, output_length is replaced by zeros in test mode.  Returns a dict."""
+    c = _Call(h)
+    B, S, W = int(h.shape[0]), int(h.shape[1]), int(beam_width)
+    if test_mode:
+        output_length = (_torch().zeros(B, dtype=_torch().int32, device=c.dev) if c.device else np.zeros(B, np.int32))
+    args = [c.inp(h, "f32"), c.inp(duration_table, "i32"), c.inp(input_length, "i32"), c.inp(output_length, "i32"),
+            c.inp(log_prob_history, "f32"), c.inp(is_finished, "bool"), c.inp(total_duration, "i32"),
+            c.inp(t, "i32"), c.inp(u, "i32")]
+    ph, p_ph = c.out((B, S, W), "i32", int(zero_duration_id))
+    bh, p_bh = c.out((B, S, W), "i32")
+    lp, p_lp = c.out((B, W), "f32")
+    ft, p_ft = c.out((B, W), "i32")
+    fu, p_fu = c.out((B, W), "i32")
+    ff, p_ff = c.out((B, W), "bool")
+    ftd, p_ftd = c.out((B, W), "i32")
+    ob, p_ob = c.out((B, W, S), "i32")
+    du, p_du = c.out((B, W, S), "i32")
+    # max_u = None: no upsampling (e.g. a loop resumed from a non-zero total_duration, whose source indexes would
+    # not start at 0)
+    up, p_up = (c.out((B, W, int(max_u)), "i32", int(out_of_range_source_index)) if max_u is not None else (None, None))
+    max_u = 0 if max_u is None else max_u
+    lib().ssnt_tts_v2_decode_loop(*args, c_int(B), c_int(S), c_int(W), c_int(int(duration_class_size)),
+                                  c_int(int(zero_duration_id)), c_bool(bool(allow_skip)), c_bool(bool(test_mode)),
+                                  c_int(int(max_u)), p_ph, p_bh, p_lp, p_ft, p_fu, p_ff, p_ftd, p_ob, p_du, p_up)
+    return {"prediction_history": ph, "beam_branch_history": bh, "log_probs": lp, "t": ft, "u": fu, "is_finished": ff,
+            "total_duration": ftd, "ordered_beam_branch": ob, "duration": du, "upsampled_source_indexes": up}
+
+
+def tone_latent_decode_loop(h, input_length, beam_width, tone_class_size, empty_tone_id,
+                            log_prob_history=None, is_finished=None, t=None, u=None):
+    """Every step of `tone_latent_beam_search_decode` (`__init__.py:99-127`) for h[B, steps, W, K] in one launch, then
+    the back-trace of every final beam and the tones along it.  Returns a dict."""
+    c = _Call(h)
+    B, S, W = int(h.shape[0]), int(h.shape[1]), int(beam_width)
+    args = [c.inp(h, "f32"), c.inp(input_length, "i32"), c.inp(log_prob_history, "f32"), c.inp(is_finished, "bool"),
+            c.inp(t, "i32"), c.inp(u, "i32")]
+    ph, p_ph = c.out((B, S, W), "i32", int(empty_tone_id))
+    bh, p_bh = c.out((B, S, W), "i32")
+    lp, p_lp = c.out((B, W), "f32")
+    ft, p_ft = c.out((B, W), "i32")
+    fu, p_fu = c.out((B, W), "i32")
+    ff, p_ff = c.out((B, W), "bool")
+    ob, p_ob = c.out((B, W, S), "i32")
+    ot, p_ot = c.out((B, W, S), "i32")
+    lib().tone_latent_decode_loop(*args, c_int(B), c_int(S), c_int(W), c_int(int(tone_class_size)),
+                                  c_int(int(empty_tone_id)), p_ph, p_bh, p_lp, p_ft, p_fu, p_ff, p_ob, p_ot)
+    return {"prediction_history": ph, "beam_branch_history": bh, "log_probs": lp, "t": ft, "u": fu, "is_finished": ff,
+            "ordered_beam_branch": ob, "ordered_tone": ot}
 
 
 # ---- lattice forward-backward (new; DESIGN.md §2) -------------------------------------------------

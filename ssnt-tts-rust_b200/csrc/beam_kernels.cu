@@ -92,17 +92,24 @@ __device__ __forceinline__ bool v2_on_diagonal(int in_len, int out_len, int next
     return diff >= -20.0f && diff <= 0.0f;
 }
 
-template <int V>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const BeamParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int b = blockIdx.x * kWarpsPerBlock + wib;
-    if (b >= p.B) return;
-    const int W = p.W, C = p.C, N = W * C;
-    // carve this warp's slice
-    const size_t per_warp = (size_t)N * (9 * 4 + 2 * 1) + 16;
-    unsigned char* base = smem + (size_t)wib * ((per_warp + 15) & ~(size_t)15);
+// One batch entry's state and result rows ([W] each; global or shared memory).
+struct BeamRow {
+    const float* h;      // [W, C]
+    const float* hist;   // [W]
+    const bool* fin;
+    const int* total;    // v2
+    const int* t;
+    const int* u;
+    int* prediction;
+    float* log_probs;
+    int* next_t;
+    int* next_u;
+    bool* next_fin;
+    int* next_total;     // v2
+    int* parent;
+};
+
+__device__ __forceinline__ Table carve_table(unsigned char* base, int N) {
     Table tb;
     tb.lp = reinterpret_cast<float*>(base);
     tb.pred = reinterpret_cast<int*>(tb.lp + N);
@@ -115,14 +122,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
     tb.key = reinterpret_cast<float*>(tb.tmp + N);
     tb.fin = reinterpret_cast<unsigned char*>(tb.key + N);
     tb.valid = tb.fin + N;
+    return tb;
+}
+__host__ __device__ inline size_t table_bytes(size_t N) { return ((N * (9 * 4 + 2) + 16) + 15) & ~(size_t)15; }
 
-    const float* h = p.h + (size_t)b * N;
-    const float* hist = p.hist + (size_t)b * W;
-    const bool* fin = p.fin + (size_t)b * W;
-    const int* tt = p.t + (size_t)b * W;
-    const int* uu = p.u + (size_t)b * W;
-    const long long in_len = V == kV1 ? (long long)p.max_t : (long long)p.in_len[b];
-    const long long out_len = V == kV2 ? (long long)p.out_len[b] : 0;
+// One beam step of one batch entry, executed by one warp.  Returns false if no candidate survived
+// (src/v2.rs:292 assert_ne! / `i % 0` in src/tone_latent.rs:199): the error flag is raised, nothing is written.
+template <int V>
+__device__ bool beam_step_warp(const BeamParams& p, const Table& tb, const BeamRow& r, long long in_len, long long out_len, int lane) {
+    const int W = p.W, C = p.C, N = W * C;
+    const float* h = r.h;
+    const float* hist = r.hist;
+    const bool* fin = r.fin;
+    const int* tt = r.t;
+    const int* uu = r.u;
 
     // ---- 1. expand ------------------------------------------------------------------------
     for (int s = lane; s < N; s += 32) {
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
                 valid = true;
                 f = true;
                 pred = V == kV1 ? 0 : p.special_id;
-                tot = V == kV2 ? p.total[(size_t)b * W + w] : 0;
+                tot = V == kV2 ? r.total[w] : 0;
             }
         } else if (V == kV1) {
             const bool last = (long long)t == in_len - 1;
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
             }
         } else if (V == kV2) {
             const int duration = p.dur_table[c];
-            tot = p.total[(size_t)b * W + w] + duration;
+            tot = r.total[w] + duration;
             int lo, hi;
             v2_bounds((int)in_len, (int)out_len, t, lo, hi);
             const unsigned long long remaining = (unsigned long long)(in_len - ((long long)t + 1));
@@ -192,14 +205,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
         if (v) {
             const int k = n + __popc(bal & ((1u << lane) - 1u));
             tb.tmp[k] = s;
-            tb.key[k] = tb.lp[s];
+            // Sort keys form a total order: the reference's comparator (partial_cmp().unwrap_or(Equal), src/lib.rs:161)
+            // leaves the position of NaN log-probs to its sort algorithm; here NaN ranks below everything, after -inf
+            // entries of the same run, so the ranks below are always a permutation.
+            const float k0 = tb.lp[s];
+            tb.key[k] = (k0 != k0) ? -INFINITY : k0;
         }
         n += __popc(bal);
     }
     __syncwarp();
     if (n == 0) {  // src/v2.rs:292 assert_ne! / `i % 0` in src/tone_latent.rs:199
         if (lane == 0) atomicOr(p.err, V == kV2 ? kErrV2EmptyBeam : kErrToneEmptyBeam);
-        return;
+        return false;
     }
     // ---- 3. stable descending sort: rank = #{j : lp_j > lp_i or (lp_j == lp_i and j before i)} ---
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -217,12 +234,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
     // ---- 4. drop consecutive duplicates (first of a run survives) ------------------------------
     int kept = 0;
     for (int r0 = 0; r0 < n; r0 += 32) {
-        const int r = r0 + lane;
+        const int q = r0 + lane;
         bool keep = false;
         int slot = 0;
-        if (r < n) {
-            slot = tb.order[r];
-            keep = r == 0 || !same_bucket(tb, slot, tb.order[r - 1]);
+        if (q < n) {
+            slot = tb.order[q];
+            keep = q == 0 || !same_bucket(tb, slot, tb.order[q - 1]);
         }
         const unsigned bal = __ballot_sync(kFull, keep);
         if (keep) tb.tmp[kept + __popc(bal & ((1u << lane) - 1u))] = slot;
@@ -233,10 +250,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
     int diag = -1;
     if (V == kV2 && !p.test_mode) {
         for (int r0 = 0; r0 < kept && diag < 0; r0 += 32) {
-            const int r = r0 + lane;
+            const int q = r0 + lane;
             bool on = false;
-            if (r < kept) {
-                const int s = tb.tmp[r];
+            if (q < kept) {
+                const int s = tb.tmp[q];
                 on = v2_on_diagonal((int)in_len, (int)out_len, tb.nt[s], tb.tot[s]);
             }
             const unsigned bal = __ballot_sync(kFull, on);
@@ -247,28 +264,196 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) beam_step_kernel(const Be
     for (int i = lane; i < W; i += 32) {
         int s = tb.tmp[i % kept];
         if (diag >= 0 && i == W - 1) s = diag;
-        const size_t o = (size_t)b * W + i;
-        p.prediction[o] = tb.pred[s];
-        p.log_probs[o] = tb.lp[s];
-        p.next_t[o] = tb.nt[s];
-        p.next_u[o] = tb.nu[s];
-        p.next_fin[o] = tb.fin[s] != 0;
-        p.parent[o] = tb.par[s];
-        if (V == kV2) p.next_total[o] = tb.tot[s];
+        r.prediction[i] = tb.pred[s];
+        r.log_probs[i] = tb.lp[s];
+        r.next_t[i] = tb.nt[s];
+        r.next_u[i] = tb.nu[s];
+        r.next_fin[i] = tb.fin[s] != 0;
+        r.parent[i] = tb.par[s];
+        if (V == kV2) r.next_total[i] = tb.tot[s];
     }
+    return true;
+}
+
+// One step for every batch entry: one warp per entry, blockDim.x / 32 entries per block.
+template <int V>
+__global__ void beam_step_kernel(const BeamParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int b = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= p.B) return;
+    const int W = p.W, N = W * p.C;
+    const Table tb = carve_table(smem + (size_t)wib * table_bytes(N), N);
+    const size_t o = (size_t)b * W;
+    BeamRow r;
+    r.h = p.h + (size_t)b * N;
+    r.hist = p.hist + o; r.fin = p.fin + o; r.total = V == kV2 ? p.total + o : nullptr; r.t = p.t + o; r.u = p.u + o;
+    r.prediction = p.prediction + o; r.log_probs = p.log_probs + o; r.next_t = p.next_t + o; r.next_u = p.next_u + o;
+    r.next_fin = p.next_fin + o; r.next_total = V == kV2 ? p.next_total + o : nullptr; r.parent = p.parent + o;
+    const long long in_len = V == kV1 ? (long long)p.max_t : (long long)p.in_len[b];
+    const long long out_len = V == kV2 ? (long long)p.out_len[b] : 0;
+    beam_step_warp<V>(p, tb, r, in_len, out_len, lane);
 }
 
 template <int V>
 void launch(const BeamParams& p, cudaStream_t stream) {
     if (p.B <= 0 || p.W <= 0) return;
-    const size_t N = (size_t)p.W * p.C;
-    const size_t per_warp = ((N * (9 * 4 + 2) + 16) + 15) & ~(size_t)15;
-    const size_t smem = per_warp * kWarpsPerBlock;
-    SSNT_ASSERT(smem <= 227 * 1024, "beam step: beam_width * classes too large for shared memory");
+    const size_t per_warp = table_bytes((size_t)p.W * p.C);
+    // Warps (batch entries) per block: four when their candidate tables fit the shared memory together, else two or one.
+    // One warp's table holds beam_width * classes up to ~6100 candidates; the reference has no limit, this library does.
+    int wpb = kWarpsPerBlock;
+    while (wpb > 1 && per_warp * wpb > 227 * 1024) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    SSNT_ASSERT(smem <= 227 * 1024, "beam step: beam_width * classes exceeds 6100 candidates (shared-memory candidate table)");
     if (smem > 48 * 1024)
         SSNT_CUDA(cudaFuncSetAttribute(beam_step_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    beam_step_kernel<V><<<blocks, 32 * kWarpsPerBlock, smem, stream>>>(p);
+    const int blocks = (p.B + wpb - 1) / wpb;
+    beam_step_kernel<V><<<blocks, 32 * wpb, smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+}
+
+// ---- whole-loop decoding -------------------------------------------------------------------
+// The reference's ABI is one call per output step (ssnt_tts_tensorflow/__init__.py:33-73, meant for a tf.while_loop),
+// followed by order_beam_branch and upsample_source_indexes (src/v2_util.rs:6-66).  When the per-step scores are known
+// up front — h [B, S, W, C] — one launch does all of it: one warp per batch entry runs the S steps with the beam state
+// in shared memory, records prediction and beam_branch per step, then walks every final beam back (final_branch =
+// 0..W-1), gathers the durations along each branch and expands them into source indexes.  Step for step it is
+// beam_step_warp above, so the results equal the per-step calls bit for bit.
+struct LoopParams {
+    BeamParams bp;            // h = [B, S, W, C]; hist/fin/total/t/u = initial state [B, W] (null: zeros / false)
+    int S, max_u;
+    int* pred_hist;           // [B, S, W]
+    int* branch_hist;         // [B, S, W]
+    int* ordered;             // [B, W, S]
+    int* ordered_pred;        // [B, W, S]  prediction along the branch (v2: mapped through the duration table → durations)
+    int* upsampled;           // [B, W, max_u] (v2, may be null), caller pre-filled
+    int hist_in_smem;         // the two histories are also kept in shared memory (back-trace without global round trips)
+};
+
+template <int V>
+__global__ void __launch_bounds__(32) decode_loop_kernel(const LoopParams lp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const BeamParams& p = lp.bp;
+    const int lane = threadIdx.x, b = blockIdx.x;
+    const int W = p.W, C = p.C, N = W * C, S = lp.S;
+    const Table tb = carve_table(smem, N);
+    // state, double-buffered: [2] x {hist f32[W], total i32[W], t i32[W], u i32[W], fin u8[W]}
+    unsigned char* sp = smem + table_bytes(N);
+    const size_t WP = (size_t)((W + 3) & ~3);
+    float* s_hist = reinterpret_cast<float*>(sp);
+    int* s_total = reinterpret_cast<int*>(s_hist + 2 * WP);
+    int* s_t = s_total + 2 * WP;
+    int* s_u = s_t + 2 * WP;
+    bool* s_fin = reinterpret_cast<bool*>(s_u + 2 * WP);
+    int* s_ph = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_fin) + 2 * WP);  // [S, W] if hist_in_smem
+    int* s_bh = s_ph + (lp.hist_in_smem ? (size_t)S * W : 0);
+    const size_t ob = (size_t)b * W;
+    for (int w = lane; w < W; w += 32) {
+        s_hist[w] = p.hist ? p.hist[ob + w] : 0.0f;
+        s_total[w] = (V == kV2 && p.total) ? p.total[ob + w] : 0;
+        s_t[w] = p.t ? p.t[ob + w] : 0;
+        s_u[w] = p.u ? p.u[ob + w] : 0;
+        s_fin[w] = p.fin ? p.fin[ob + w] : false;
+    }
+    __syncwarp();
+    const long long in_len = (long long)p.in_len[b];
+    const long long out_len = V == kV2 ? (long long)p.out_len[b] : 0;
+    int* gph = lp.pred_hist + (size_t)b * S * W;
+    int* gbh = lp.branch_hist + (size_t)b * S * W;
+    int cur = 0;
+    for (int s = 0; s < S; ++s) {
+        const int nxt = cur ^ 1;
+        BeamRow r;
+        r.h = p.h + ((size_t)b * S + s) * N;
+        r.hist = s_hist + cur * WP; r.fin = s_fin + cur * WP; r.total = s_total + cur * WP; r.t = s_t + cur * WP; r.u = s_u + cur * WP;
+        r.prediction = lp.hist_in_smem ? s_ph + (size_t)s * W : gph + (size_t)s * W;
+        r.parent = lp.hist_in_smem ? s_bh + (size_t)s * W : gbh + (size_t)s * W;
+        r.log_probs = s_hist + nxt * WP; r.next_t = s_t + nxt * WP; r.next_u = s_u + nxt * WP;
+        r.next_fin = s_fin + nxt * WP; r.next_total = s_total + nxt * WP;
+        if (!beam_step_warp<V>(p, tb, r, in_len, out_len, lane)) return;  // flag raised; the reference would have panicked here
+        __syncwarp();
+        if (lp.hist_in_smem)
+            for (int w = lane; w < W; w += 32) {
+                gph[(size_t)s * W + w] = s_ph[(size_t)s * W + w];
+                gbh[(size_t)s * W + w] = s_bh[(size_t)s * W + w];
+            }
+        cur = nxt;
+    }
+    // final state
+    for (int w = lane; w < W; w += 32) {
+        p.log_probs[ob + w] = s_hist[cur * WP + w];
+        p.next_t[ob + w] = s_t[cur * WP + w];
+        p.next_u[ob + w] = s_u[cur * WP + w];
+        p.next_fin[ob + w] = s_fin[cur * WP + w];
+        if (V == kV2) p.next_total[ob + w] = s_total[cur * WP + w];
+    }
+    __syncwarp();
+    __threadfence_block();
+    // back-trace of every final beam (src/v2_util.rs:26-36 with final_branch = w): a lane per beam
+    for (int w = lane; w < W; w += 32) {
+        int c = w;
+        int* ord = lp.ordered + ((size_t)b * W + w) * S;
+        int* opr = lp.ordered_pred + ((size_t)b * W + w) * S;
+        for (int s = S - 1; s >= 0; --s) {
+            const int pr = lp.hist_in_smem ? s_ph[(size_t)s * W + c] : __ldcg(gph + (size_t)s * W + c);
+            const int par = lp.hist_in_smem ? s_bh[(size_t)s * W + c] : __ldcg(gbh + (size_t)s * W + c);
+            ord[s] = c;
+            opr[s] = V == kV2 ? p.dur_table[pr] : pr;
+            c = par;  // always in [0, W): written by beam_step_warp
+        }
+    }
+    if (V != kV2 || lp.upsampled == nullptr) return;
+    __syncwarp();
+    __threadfence_block();
+    // source indexes: index s repeated duration[s] times (src/v2_util.rs:39-66); length = the beam's total duration
+    for (int w = 0; w < W; ++w) {
+        const int* d = lp.ordered_pred + ((size_t)b * W + w) * S;
+        const int len = s_total[cur * WP + w];
+        int total = 0;
+        bool bad = false;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int v = s0 + lane < S ? __ldcg(d + s0 + lane) : 0;
+            bad |= v < 0;
+            total += v > 0 ? v : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+        if (__any_sync(kFull, bad) || total != len) {  // assert_eq!(upsampled.len(), output_length[0]) src/v2_util.rs:58
+            if (lane == 0) atomicOr(p.err, kErrUpsampleLength);
+            continue;
+        }
+        int* out = lp.upsampled + ((size_t)b * W + w) * lp.max_u;
+        int base = 0;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int s = s0 + lane;
+            const int v = s < S ? __ldcg(d + s) : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFull, x, o);
+                if (lane >= o) x += y;
+            }
+            const int start = base + x - v;
+            for (int k = 0; k < v && start + k < lp.max_u; ++k) out[start + k] = s;
+            base += __shfl_sync(kFull, x, 31);
+        }
+    }
+}
+
+template <int V>
+void launch_loop(LoopParams lp, cudaStream_t stream) {
+    const BeamParams& p = lp.bp;
+    if (p.B <= 0 || p.W <= 0 || lp.S <= 0) return;
+    const size_t WP = (size_t)((p.W + 3) & ~3);
+    const size_t base = table_bytes((size_t)p.W * p.C) + 2 * WP * (4 * 4 + 1) + 16;
+    const size_t hist = (size_t)2 * lp.S * p.W * sizeof(int);
+    lp.hist_in_smem = base + hist <= 200 * 1024 ? 1 : 0;
+    const size_t smem = base + (lp.hist_in_smem ? hist : 0);
+    SSNT_ASSERT(smem <= 227 * 1024, "decode loop: beam_width * classes exceeds 6000 candidates (shared-memory candidate table)");
+    if (smem > 48 * 1024)
+        SSNT_CUDA(cudaFuncSetAttribute(decode_loop_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decode_loop_kernel<V><<<p.B, 32, smem, stream>>>(lp);
     SSNT_CUDA(cudaGetLastError());
 }
 
@@ -317,6 +502,43 @@ void tone_beam_search_decode(const float* h, const float* hist, const bool* fin,
     p.next_fin = next_fin; p.parent = parent; p.err = device_error_flag();
     SSNT_ASSERT(classes > 0, "tone_class_size must be positive");
     launch<kTone>(p, stream);
+}
+
+void v2_decode_loop(const float* h, const int* dur_table, const int* in_len, const int* out_len, const float* hist0,
+                    const bool* fin0, const int* total0, const int* t0, const int* u0, int batch_size, int steps,
+                    int beam_width, int classes, int zero_duration_id, bool allow_skip, bool test_mode, int max_u,
+                    int* pred_hist, int* branch_hist, float* log_probs, int* final_t, int* final_u, bool* final_fin,
+                    int* final_total, int* ordered, int* duration, int* upsampled, cudaStream_t stream) {
+    LoopParams lp{};
+    BeamParams& p = lp.bp;
+    p.h = h; p.hist = hist0; p.fin = fin0; p.total = total0; p.dur_table = dur_table; p.t = t0; p.u = u0;
+    p.in_len = in_len; p.out_len = out_len;
+    p.B = batch_size; p.W = beam_width; p.C = classes; p.special_id = zero_duration_id;
+    p.allow_skip = allow_skip; p.test_mode = test_mode;
+    p.log_probs = log_probs; p.next_t = final_t; p.next_u = final_u; p.next_fin = final_fin; p.next_total = final_total;
+    p.err = device_error_flag();
+    lp.S = steps; lp.max_u = max_u;
+    lp.pred_hist = pred_hist; lp.branch_hist = branch_hist; lp.ordered = ordered; lp.ordered_pred = duration;
+    lp.upsampled = upsampled;
+    SSNT_ASSERT(classes > 0, "duration_class_size must be positive");
+    launch_loop<kV2>(lp, stream);
+}
+
+void tone_decode_loop(const float* h, const int* in_len, const float* hist0, const bool* fin0, const int* t0, const int* u0,
+                      int batch_size, int steps, int beam_width, int classes, int empty_tone_id, int* pred_hist,
+                      int* branch_hist, float* log_probs, int* final_t, int* final_u, bool* final_fin, int* ordered,
+                      int* ordered_tone, cudaStream_t stream) {
+    LoopParams lp{};
+    BeamParams& p = lp.bp;
+    p.h = h; p.hist = hist0; p.fin = fin0; p.t = t0; p.u = u0; p.in_len = in_len;
+    p.B = batch_size; p.W = beam_width; p.C = classes; p.special_id = empty_tone_id;
+    p.log_probs = log_probs; p.next_t = final_t; p.next_u = final_u; p.next_fin = final_fin;
+    p.err = device_error_flag();
+    lp.S = steps; lp.max_u = 0;
+    lp.pred_hist = pred_hist; lp.branch_hist = branch_hist; lp.ordered = ordered; lp.ordered_pred = ordered_tone;
+    lp.upsampled = nullptr;
+    SSNT_ASSERT(classes > 0, "tone_class_size must be positive");
+    launch_loop<kTone>(lp, stream);
 }
 
 }  // namespace ssnt

@@ -24,6 +24,11 @@ void extract_best_beam_branch(int, const int*, const int*, int, int, int*, int*,
 void order_beam_branch(const int*, const int*, int, int, int, int*, cudaStream_t);
 void upsample_source_indexes(const int*, const int*, int, int, int, int, int*, cudaStream_t);
 void levenshtein_edit_distance(const int*, const int*, const int*, const int*, int, int, int*, cudaStream_t);
+void v2_decode_loop(const float*, const int*, const int*, const int*, const float*, const bool*, const int*, const int*,
+                    const int*, int, int, int, int, int, bool, bool, int, int*, int*, float*, int*, int*, bool*, int*, int*,
+                    int*, int*, cudaStream_t);
+void tone_decode_loop(const float*, const int*, const float*, const bool*, const int*, const int*, int, int, int, int, int,
+                      int*, int*, float*, int*, int*, bool*, int*, int*, cudaStream_t);
 
 namespace {
 
@@ -38,6 +43,7 @@ public:
     HostCall() : stream_(current_stream()) {}
     template <typename T>
     const T* in(const T* host, size_t n) {
+        if (!host) return nullptr;  // optional argument
         T* d = (T*)device_scratch(slot_++, n * sizeof(T) + 16);
         if (n) SSNT_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, stream_));
         return d;
@@ -45,6 +51,7 @@ public:
     // preload = the callee leaves some slots untouched, so the caller's pre-fill must survive
     template <typename T>
     T* out(T* host, size_t n, bool preload = false) {
+        if (!host) return nullptr;  // optional argument
         T* d = (T*)device_scratch(slot_++, n * sizeof(T) + 16);
         if (preload && n) SSNT_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, stream_));
         outs_.push_back({d, host, n * sizeof(T)});
@@ -326,6 +333,69 @@ void tone_latent_levenshtein_edit_distance(const int* a, const int* b, const int
     auto dal = c.in(a_lengths, B); auto dbl = c.in(b_lengths, B);
     auto od = c.out(distance, B);
     levenshtein_edit_distance(da, db, dal, dbl, batch_size, max_length, od, c.stream());
+    c.finish();
+}
+
+// ---- whole-loop decoding (no counterpart in the reference's ABI: SURVEY.md §8 f2) ------------------------------
+void ssnt_tts_v2_decode_loop(const float* h, const int* duration_table, const int* input_length, const int* output_length,
+                             const float* log_prob_history, const bool* is_finished, const int* total_duration,
+                             const int* t, const int* u, int batch_size, int steps, int beam_width,
+                             int duration_class_size, int zero_duration_id, bool allow_skip, bool test_mode, int max_u,
+                             int* prediction_history, int* beam_branch_history, float* log_probs, int* final_t,
+                             int* final_u, bool* final_is_finished, int* final_total_duration, int* ordered_beam_branch,
+                             int* duration, int* upsampled_source_indexes) {
+    NOT_NULL(h); NOT_NULL(duration_table); NOT_NULL(input_length); NOT_NULL(output_length);
+    NOT_NULL(prediction_history); NOT_NULL(beam_branch_history); NOT_NULL(log_probs); NOT_NULL(final_t); NOT_NULL(final_u);
+    NOT_NULL(final_is_finished); NOT_NULL(final_total_duration); NOT_NULL(ordered_beam_branch); NOT_NULL(duration);
+    const size_t BW = n2(batch_size, beam_width), B = (size_t)(batch_size > 0 ? batch_size : 0);
+    const size_t BSW = BW * (size_t)(steps > 0 ? steps : 0);
+    if (is_device_pointer(h)) {
+        v2_decode_loop(h, duration_table, input_length, output_length, log_prob_history, is_finished, total_duration, t, u,
+                       batch_size, steps, beam_width, duration_class_size, zero_duration_id, allow_skip, test_mode, max_u,
+                       prediction_history, beam_branch_history, log_probs, final_t, final_u, final_is_finished,
+                       final_total_duration, ordered_beam_branch, duration, upsampled_source_indexes, current_stream());
+        return;
+    }
+    HostCall c;
+    auto dh = c.in(h, BSW * (size_t)(duration_class_size > 0 ? duration_class_size : 0));
+    auto dtab = c.in(duration_table, (size_t)(duration_class_size > 0 ? duration_class_size : 0));
+    auto dil = c.in(input_length, B); auto dol = c.in(output_length, B);
+    auto dl = c.in(log_prob_history, BW); auto df = c.in(is_finished, BW); auto dtd = c.in(total_duration, BW);
+    auto dt = c.in(t, BW); auto du = c.in(u, BW);
+    auto oph = c.out(prediction_history, BSW); auto obh = c.out(beam_branch_history, BSW);
+    auto ol = c.out(log_probs, BW); auto ot = c.out(final_t, BW); auto ou = c.out(final_u, BW);
+    auto of = c.out(final_is_finished, BW); auto otd = c.out(final_total_duration, BW);
+    auto oo = c.out(ordered_beam_branch, BSW); auto od = c.out(duration, BSW);
+    auto oup = c.out(upsampled_source_indexes, BW * (size_t)(max_u > 0 ? max_u : 0), /*preload=*/true);
+    v2_decode_loop(dh, dtab, dil, dol, dl, df, dtd, dt, du, batch_size, steps, beam_width, duration_class_size,
+                   zero_duration_id, allow_skip, test_mode, max_u, oph, obh, ol, ot, ou, of, otd, oo, od, oup, c.stream());
+    c.finish();
+}
+
+void tone_latent_decode_loop(const float* h, const int* input_length, const float* log_prob_history, const bool* is_finished,
+                             const int* t, const int* u, int batch_size, int steps, int beam_width, int tone_class_size,
+                             int empty_tone_id, int* prediction_history, int* beam_branch_history, float* log_probs,
+                             int* final_t, int* final_u, bool* final_is_finished, int* ordered_beam_branch,
+                             int* ordered_tone) {
+    NOT_NULL(h); NOT_NULL(input_length); NOT_NULL(prediction_history); NOT_NULL(beam_branch_history); NOT_NULL(log_probs);
+    NOT_NULL(final_t); NOT_NULL(final_u); NOT_NULL(final_is_finished); NOT_NULL(ordered_beam_branch); NOT_NULL(ordered_tone);
+    const size_t BW = n2(batch_size, beam_width), B = (size_t)(batch_size > 0 ? batch_size : 0);
+    const size_t BSW = BW * (size_t)(steps > 0 ? steps : 0);
+    if (is_device_pointer(h)) {
+        tone_decode_loop(h, input_length, log_prob_history, is_finished, t, u, batch_size, steps, beam_width, tone_class_size,
+                         empty_tone_id, prediction_history, beam_branch_history, log_probs, final_t, final_u,
+                         final_is_finished, ordered_beam_branch, ordered_tone, current_stream());
+        return;
+    }
+    HostCall c;
+    auto dh = c.in(h, BSW * (size_t)(tone_class_size > 0 ? tone_class_size : 0));
+    auto dil = c.in(input_length, B);
+    auto dl = c.in(log_prob_history, BW); auto df = c.in(is_finished, BW); auto dt = c.in(t, BW); auto du = c.in(u, BW);
+    auto oph = c.out(prediction_history, BSW); auto obh = c.out(beam_branch_history, BSW);
+    auto ol = c.out(log_probs, BW); auto ot = c.out(final_t, BW); auto ou = c.out(final_u, BW);
+    auto of = c.out(final_is_finished, BW); auto oo = c.out(ordered_beam_branch, BSW); auto od = c.out(ordered_tone, BSW);
+    tone_decode_loop(dh, dil, dl, df, dt, du, batch_size, steps, beam_width, tone_class_size, empty_tone_id, oph, obh, ol, ot,
+                     ou, of, oo, od, c.stream());
     c.finish();
 }
 

@@ -324,3 +324,154 @@ def test_config4_pipeline_end_to_end(product, oracle_mod):
     want = oracle_mod.levenshtein_edit_distance(dur_o[:, 0], ref, lens, lens)
     got = product.levenshtein_edit_distance(dur_d[:, 0].contiguous(), _dev(ref), _dev(lens), _dev(lens))
     _eq(got, want)
+
+
+# ---------------------------------------------------------------- whole-loop decoding
+def _oracle_v2_loop(oracle_mod, h, table, in_len, out_len, W, D, zero_id, allow_skip, test_mode, max_u, fill):
+    """The reference's usage restated with the oracle: one v2 step per output frame (`__init__.py:33-73`), then
+    order_beam_branch with final_branch = 0..W-1, the durations along each branch, upsample_source_indexes."""
+    B, S = h.shape[0], h.shape[1]
+    lph = np.zeros((B, W), np.float32); fin = np.zeros((B, W), np.bool_); tot = np.zeros((B, W), np.int32)
+    t = np.zeros((B, W), np.int32); u = np.zeros((B, W), np.int32)
+    ol = np.zeros_like(out_len) if test_mode else out_len
+    preds, parents = [], []
+    for s in range(S):
+        *o, bad = oracle_mod.ssnt_tts_v2_beam_search_decode(np.ascontiguousarray(h[:, s]), lph, fin, tot, table, t, u,
+                                                          in_len, ol, W, D, zero_id, allow_skip, test_mode)
+        if bad:
+            return None
+        pred, lph, t, u, fin, tot, parent = o
+        preds.append(pred); parents.append(parent)
+    ph, bh = np.stack(preds, axis=1), np.stack(parents, axis=1)          # (B, S, W)
+    final = np.tile(np.arange(W, dtype=np.int32), (B, 1))
+    ordered = oracle_mod.order_beam_branch(final, bh, W)                  # (B, W, S)
+    dur = np.stack([[table[ph[b, np.arange(S), ordered[b, w]]] for w in range(W)] for b in range(B)]).astype(np.int32)
+    up, bad = oracle_mod.upsample_source_indexes(dur, tot, fill, W, max_u=max_u)
+    assert bad == 0
+    return dict(prediction_history=ph, beam_branch_history=bh, log_probs=lph, t=t, u=u, is_finished=fin,
+                total_duration=tot, ordered_beam_branch=ordered, duration=dur, upsampled_source_indexes=up)
+
+
+@pytest.mark.parametrize("B,W,D,in_hi,allow_skip,test_mode,quant", [
+    (64, 8, 16, 150, False, False, False),    # BASELINE configs[3]: beam 8, B=64, 150 tokens, <= 1000 frames
+    (5, 8, 32, 40, True, False, False),
+    (4, 4, 8, 10, False, True, False),
+    (3, 6, 8, 12, True, False, True),
+    (2, 33, 12, 9, False, False, False),
+])
+def test_v2_whole_loop_equals_per_step_calls(product, oracle_mod, space, B, W, D, in_hi, allow_skip, test_mode, quant):
+    rng = np.random.default_rng(B * 131 + W * 17 + D + 1)
+    in_len, out_len, table = _v2_case(rng, B, W, D, in_hi, quant)
+    S = int(in_len.max()) + 2
+    if quant:
+        h = np.log(rng.choice([0.05, 0.1, 0.2], size=(B, S, W, D))).astype(np.float32)
+    else:
+        h = _log_softmax(rng.standard_normal((B, S, W, D)))
+    max_u = 1000 if in_hi == 150 else int(out_len.max()) + 8
+    want = _oracle_v2_loop(oracle_mod, h, table, in_len, out_len, W, D, 0, allow_skip, test_mode, max_u, -7)
+    assert want is not None, "case must be decodable"
+    if space == "device":
+        product.last_error()
+    got = product.ssnt_tts_v2_decode_loop(*_conv(space, h, table, in_len, out_len), W, D, 0, allow_skip, test_mode,
+                                          max_u, -7)
+    if space == "device":
+        assert product.last_error() == 0
+    for k, w in want.items():
+        _eq(got[k], w, k)
+    assert want["is_finished"].all()
+
+
+def test_v2_whole_loop_takes_an_initial_state(product, oracle_mod):
+    """Resuming: the loop over steps [s0, S) from the state after s0 per-step calls equals the tail of the full loop."""
+    rng = np.random.default_rng(11)
+    B, W, D, S, s0 = 6, 8, 16, 30, 11
+    in_len, out_len, table = _v2_case(rng, B, W, D, 28, False)
+    h = _log_softmax(rng.standard_normal((B, S, W, D)))
+    product.last_error()
+    run = lambda hh, **state: product.ssnt_tts_v2_decode_loop(*(_dev(a) for a in (hh, table, in_len, out_len)), W, D, 0,
+                                                              True, True, None, -1, **state)
+    full = run(h)
+    head = run(h[:, :s0])
+    tail = run(h[:, s0:], log_prob_history=head["log_probs"], is_finished=head["is_finished"],
+               total_duration=head["total_duration"], t=head["t"], u=head["u"])
+    assert product.last_error() == 0
+    for k in ("log_probs", "t", "u", "is_finished", "total_duration"):
+        _eq(tail[k], _np(full[k]), k)
+    _eq(tail["prediction_history"], _np(full["prediction_history"])[:, s0:])
+    _eq(tail["beam_branch_history"], _np(full["beam_branch_history"])[:, s0:])
+
+
+@pytest.mark.parametrize("B,W,K,in_hi", [(64, 8, 4, 150), (3, 5, 1, 6), (2, 40, 7, 9)])
+def test_tone_whole_loop_equals_per_step_calls(product, oracle_mod, space, B, W, K, in_hi):
+    rng = np.random.default_rng(B * 7 + W + K + 1)
+    in_len = rng.integers(1, in_hi + 1, B).astype(np.int32)
+    S = in_hi + 2
+    h = _log_softmax(rng.standard_normal((B, S, W, K)))
+    h[:, 2::3] = np.round(h[:, 2::3] * 2) / 2   # provoke ties
+    lph = np.zeros((B, W), np.float32); fin = np.zeros((B, W), np.bool_)
+    t = np.zeros((B, W), np.int32); u = np.zeros((B, W), np.int32)
+    preds, parents = [], []
+    for s in range(S):
+        pred, lph, t, u, fin, parent = oracle_mod.tone_latent_beam_search_decode(np.ascontiguousarray(h[:, s]), lph, fin, t, u,
+                                                                                 in_len, W, K, K)
+        preds.append(pred); parents.append(parent)
+    ph, bh = np.stack(preds, axis=1), np.stack(parents, axis=1)
+    ordered = oracle_mod.order_beam_branch(np.tile(np.arange(W, dtype=np.int32), (B, 1)), bh, W)
+    tones = np.stack([[ph[b, np.arange(S), ordered[b, w]] for w in range(W)] for b in range(B)]).astype(np.int32)
+    got = product.tone_latent_decode_loop(*_conv(space, h, in_len), W, K, K)
+    for k, w in dict(prediction_history=ph, beam_branch_history=bh, log_probs=lph, t=t, u=u, is_finished=fin,
+                     ordered_beam_branch=ordered, ordered_tone=tones).items():
+        _eq(got[k], w, k)
+
+
+def test_v2_whole_loop_empty_beam_raises_the_flag(product):
+    B, W, D, S = 2, 4, 4, 3
+    h = np.zeros((B, S, W, D), np.float32)
+    table = np.array([0, 50, 60, 70], np.int32)     # every class pruned by the band → src/v2.rs:292 assert_ne!
+    in_len, out_len = np.array([10, 10], np.int32), np.array([20, 20], np.int32)
+    product.last_error()
+    product.ssnt_tts_v2_decode_loop(*(_dev(a) for a in (h, table, in_len, out_len)), W, D, 0, False, False, 16, -1)
+    assert product.last_error() & product.ERR_V2_EMPTY_BEAM
+
+
+# ---------------------------------------------------------------- robustness (ADVICE.md round 1)
+def test_beam_step_with_nan_and_inf_scores_does_not_corrupt(product, oracle_mod):
+    """inf - inf / NaN logits: the reference's comparator treats NaN as Equal (src/lib.rs:161) and leaves their final
+    position to its sort algorithm, but never crashes.  Here NaN ranks below everything: every output slot is a real
+    candidate (valid parent, valid class), and rows without NaN still equal the oracle exactly."""
+    rng = np.random.default_rng(3)
+    B, W, K = 6, 8, 5
+    h = _log_softmax(rng.standard_normal((B, W, K)))
+    h[0, 2, 1] = np.nan; h[0, 5, :] = np.nan; h[1, :, 3] = -np.inf; h[2, 0, 0] = np.inf; h[3] = np.nan
+    lph = np.zeros((B, W), np.float32); lph[1, 3] = -np.inf; lph[2, 1] = np.inf
+    fin = np.zeros((B, W), np.bool_); z = np.zeros((B, W), np.int32); in_len = np.full(B, 9, np.int32)
+    product.last_error()
+    got = product.tone_latent_beam_search_decode(*(_dev(a) for a in (h, lph, fin, z, z, in_len)), W, K, K)
+    assert product.last_error() == 0
+    pred, lp, nt, nu, nf, parent = (_np(g) for g in got)
+    assert ((parent >= 0) & (parent < W)).all() and ((pred >= 0) & (pred < K)).all()
+    assert (nt == 1).all() and (nu == 1).all()
+    want = oracle_mod.tone_latent_beam_search_decode(h, lph, fin, z, z, in_len, W, K, K)
+    for b in (4, 5):   # rows without NaN
+        for g, w in zip((pred, lp, nt, nu, nf, parent), want):
+            _eq(g[b], w[b])
+    # rows 1 and 2 hold infinities but no NaN: a total order exists, so they must match too
+    for b in (1,):
+        for g, w in zip((pred, lp, nt, nu, nf, parent), want):
+            _eq(g[b], w[b])
+
+
+def test_wide_candidate_tables_run_with_fewer_warps_per_block(product, oracle_mod):
+    """beam_width * classes beyond four tables' worth of shared memory (W=32, D=64: 2048 candidates) used to abort."""
+    rng = np.random.default_rng(8)
+    B, W, D = 3, 32, 64
+    h = _log_softmax(rng.standard_normal((B, W, D)))
+    lph = np.zeros((B, W), np.float32); fin = np.zeros((B, W), np.bool_); z = np.zeros((B, W), np.int32)
+    table = np.arange(D, dtype=np.int32)
+    in_len, out_len = np.full(B, 12, np.int32), np.full(B, 60, np.int32)
+    *want, bad = oracle_mod.ssnt_tts_v2_beam_search_decode(h, lph, fin, z, table, z, z, in_len, out_len, W, D, 0, False, True)
+    assert bad == 0
+    got = product.ssnt_tts_v2_beam_search_decode(*(_dev(a) for a in (h, lph, fin, z, table, z, z, in_len, out_len)),
+                                                 W, D, 0, False, True)
+    for g, w in zip(got, want):
+        _eq(g, w)
