@@ -120,6 +120,17 @@ void ssnt_tts_forward_backward(const float *log_emit, const float *log_shift, co
                                float *log_likelihood, float *loss, float *grad_emit,
                                float *grad_shift, void *workspace, size_t workspace_bytes);
 
+/* Raw-logit variant of ssnt_tts_forward_backward for models whose emit/shift scores are the two-way split of ONE logit,
+ * log_emit = log sigmoid(z), log_shift = log sigmoid(-z) (the reference's rows are such two-way distributions,
+ * tests/test_decoding.rs:25-29): the log-sigmoids are formed inside the kernels' loads and the gradient is chained
+ * through them, grad_logits = dLL/dz = grad_emit * sigmoid(-z) - grad_shift * sigmoid(z).  logits, grad_logits [B,T,U];
+ * everything else as ssnt_tts_forward_backward.  Results equal that call on (log sigmoid(z), log sigmoid(-z)) to
+ * rounding.  12 bytes per lattice cell cross the memory bus instead of 16. */
+size_t ssnt_tts_forward_backward_logits_workspace_bytes(int batch_size, int max_t, int max_u);
+void ssnt_tts_forward_backward_logits(const float *logits, const int *t_len, const int *u_len, int batch_size,
+                                      int max_t, int max_u, float *log_likelihood, float *loss,
+                                      float *grad_logits, void *workspace, size_t workspace_bytes);
+
 /* Tone-latent marginalised lattice: log_emit/log_shift [B,max_t,max_u,K], log_tone [B,max_u,K]
  * (log-prior of each token's tone class; cf. tone_class_size of src/tone_latent.rs:79-95). */
 size_t tone_latent_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u,

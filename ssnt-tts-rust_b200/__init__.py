@@ -52,6 +52,8 @@ C_SYMBOLS = (
     "ssnt_tts_backend",
     "ssnt_tts_debug_host_copy",
     "ssnt_tts_v2_decode_loop",
+    "ssnt_tts_forward_backward_logits_workspace_bytes",
+    "ssnt_tts_forward_backward_logits",
     "tone_latent_decode_loop",
     "ssnt_tts_loss_exchange_export",
     "ssnt_tts_loss_exchange_connect",
@@ -87,6 +89,8 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.ssnt_tts_forward_backward_workspace_bytes.restype = c_size_t
         L.ssnt_tts_forward_backward_workspace_bytes.argtypes = [c_int, c_int, c_int]
+        L.ssnt_tts_forward_backward_logits_workspace_bytes.restype = c_size_t
+        L.ssnt_tts_forward_backward_logits_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.tone_latent_forward_backward_workspace_bytes.restype = c_size_t
         L.tone_latent_forward_backward_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
         L.ssnt_tts_get_stream.restype = c_void_p
@@ -381,6 +385,34 @@ def forward_backward(log_emit, log_shift, t_len=None, u_len=None, workspace=None
     lib().ssnt_tts_forward_backward(a_le, a_ls, a_tl, a_ul, c_int(B), c_int(T), c_int(U), p_ll, p_loss,
                                     p_ge, p_gs, ws_ptr, c_size_t(ws_bytes))
     return ll, loss, ge, gs
+
+
+def forward_backward_logits_workspace_bytes(batch_size, max_t, max_u) -> int:
+    return int(lib().ssnt_tts_forward_backward_logits_workspace_bytes(batch_size, max_t, max_u))
+
+
+def forward_backward_logits(logits, t_len=None, u_len=None, workspace=None, out=None):
+    """The lattice on raw logits: log_emit = log sigmoid(z), log_shift = log sigmoid(-z) formed inside the kernels,
+    gradient chained through them.  logits: [B, T, U] fp32.  Returns (log_likelihood[B], loss[1], grad_logits[B, T, U])
+    with grad_logits = d log_likelihood / d z = grad_emit * sigmoid(-z) - grad_shift * sigmoid(z)."""
+    c = _Call(logits)
+    B, T, U = (int(s) for s in logits.shape)
+    a_z = c.inp(logits, "f32")
+    a_tl, a_ul = c.inp(t_len, "i32"), c.inp(u_len, "i32")
+    if out is not None:
+        ll, loss, gz = out
+        ptr = (lambda x: c_void_p(x.data_ptr())) if c.device else (lambda x: c_void_p(x.ctypes.data))
+        p_ll, p_loss, p_gz = ptr(ll), ptr(loss), ptr(gz)
+    else:
+        ll, p_ll = c.out((B,), "f32")
+        loss, p_loss = c.out((1,), "f32")
+        gz, p_gz = c.out((B, T, U), "f32")
+    ws_ptr, ws_bytes = c_void_p(0), 0
+    if workspace is not None:
+        ws_ptr, ws_bytes = c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
+    lib().ssnt_tts_forward_backward_logits(a_z, a_tl, a_ul, c_int(B), c_int(T), c_int(U), p_ll, p_loss, p_gz,
+                                           ws_ptr, c_size_t(ws_bytes))
+    return ll, loss, gz
 
 
 def tone_latent_forward_backward_workspace_bytes(batch_size, max_t, max_u, tone_class_size) -> int:

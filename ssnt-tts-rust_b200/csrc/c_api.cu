@@ -451,6 +451,60 @@ void ssnt_tts_forward_backward(const float* log_emit, const float* log_shift, co
     }
 }
 
+// Raw-logit entry: log_emit = log sigmoid(z), log_shift = log sigmoid(-z) fused into the kernels' loads,
+// the gradient chained through them.  12 bytes per lattice cell cross the memory bus instead of 16 (plus the upstream
+// log_sigmoid kernels' own traffic, which disappears).
+size_t ssnt_tts_forward_backward_logits_workspace_bytes(int batch_size, int max_t, int max_u) {
+    return fb_logits_workspace_bytes(batch_size, max_t, max_u);
+}
+
+void ssnt_tts_forward_backward_logits(const float* logits, const int* t_len, const int* u_len, int batch_size, int max_t,
+                                      int max_u, float* log_likelihood, float* loss, float* grad_logits, void* workspace,
+                                      size_t workspace_bytes) {
+    NOT_NULL(logits); NOT_NULL(log_likelihood); NOT_NULL(grad_logits);
+    if (is_device_pointer(logits)) {
+        FbArgs a{nullptr, nullptr, t_len, u_len, batch_size, max_t, max_u, log_likelihood, loss, nullptr, nullptr, workspace,
+                 workspace_bytes};
+        a.logits = logits;
+        a.grad_logits = grad_logits;
+        launch_forward_backward(a, current_stream());
+        return;
+    }
+    // Host buffers: the chunked staging pipeline of ssnt_tts_forward_backward, one tensor each way.
+    const size_t slab = n2(max_t, max_u) * sizeof(float);
+    const int B = batch_size > 0 ? batch_size : 0;
+    const size_t per_b = 2 * slab + 3 * sizeof(int);
+    const int pass_b = per_b * B <= kStageBytes ? B : (int)(kStageBytes / per_b > 0 ? kStageBytes / per_b : 1);
+    for (int p0 = 0; p0 < B; p0 += pass_b) {
+        const int nb_pass = p0 + pass_b <= B ? pass_b : B - p0;
+        const size_t o = (size_t)p0 * (slab / sizeof(float));
+        std::vector<HostArray> ins = {{logits + o, nullptr, slab, 4}};
+        if (t_len) ins.push_back({t_len + p0, nullptr, sizeof(int), 9});
+        if (u_len) ins.push_back({u_len + p0, nullptr, sizeof(int), 10});
+        std::vector<HostArray> outs = {{nullptr, grad_logits + o, slab, 6}, {nullptr, log_likelihood + p0, sizeof(float), 8}};
+        const int nchunks = lattice_chunks(nb_pass, slab * nb_pass);
+        const int per = (nb_pass + nchunks - 1) / nchunks;
+        const size_t ws_each = (fb_logits_workspace_bytes(per, max_t, max_u) + 255) & ~(size_t)255;
+        char* ws = (char*)device_scratch(0, ws_each * nchunks);
+        const int i_tl = t_len ? 1 : -1, i_ul = u_len ? (t_len ? 2 : 1) : -1;
+        staged_lattice_pass(ins, outs, nb_pass, nchunks, [&](int b0, int nb, int c, cudaStream_t s) {
+            const size_t e = (size_t)b0 * (slab / sizeof(float));
+            FbArgs a{nullptr, nullptr, i_tl >= 0 ? (const int*)ins[i_tl].dev + b0 : nullptr,
+                     i_ul >= 0 ? (const int*)ins[i_ul].dev + b0 : nullptr, nb, max_t, max_u, (float*)outs[1].dev + b0, nullptr,
+                     nullptr, nullptr, ws + (size_t)c * ws_each, ws_each};
+            a.logits = (const float*)ins[0].dev + e;
+            a.grad_logits = (float*)outs[0].dev + e;
+            launch_forward_backward(a, s);
+        });
+    }
+    check_error_flag_or_panic();
+    if (loss) {
+        double acc = 0.0;  // loss = -sum_b ll[b] in batch order, in double (as the kernel's own reduction)
+        for (int b2 = 0; b2 < B; ++b2) acc -= (double)log_likelihood[b2];
+        *loss = (float)acc;
+    }
+}
+
 size_t tone_latent_forward_backward_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size) {
     return tone_fb_workspace_bytes(batch_size, max_t, max_u, tone_class_size);
 }

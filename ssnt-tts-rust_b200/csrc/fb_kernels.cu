@@ -15,7 +15,6 @@
 //            domain with one integer offset per token.
 #include "fb_split.cuh"
 #include "fb_tp.cuh"
-#include "fb_tp4.cuh"
 
 namespace ssnt {
 namespace {
@@ -44,9 +43,12 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
     } else if (T <= 0 || U <= 0 || U > T) {
         // No monotonic path: ll = -inf, every gradient 0.  Uniform for both CTAs of the cluster.
         const size_t slab = (size_t)a.max_t * a.max_u;
-        float* g = (rank == 0 ? a.grad_emit : a.grad_shift) + (size_t)b * slab;
+        float* g = a.logits ? (rank == 0 ? a.grad_logits : nullptr) : (rank == 0 ? a.grad_emit : a.grad_shift);
         const float zeros[CPL] = {};
-        for (int t = 0; t < a.max_t; ++t) store_cells_cs<CPL>(g + (size_t)t * a.max_u, lane * CPL, a.max_u, zeros);
+        if (g) {
+            g += (size_t)b * slab;
+            for (int t = 0; t < a.max_t; ++t) store_cells_cs<CPL>(g + (size_t)t * a.max_u, lane * CPL, a.max_u, zeros);
+        }
         if (rank == 0 && lane == 0) a.log_likelihood[b] = -INFINITY;
     } else {
         if (p.only && rank == 0 && lane == 0) atomicAdd(p.fallbacks, 1u);
@@ -404,7 +406,11 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     TpParams pg = p;
     pg.G = G;
     const TpParams& p2 = pg;
-    if (stages >= 1) tp_build_kernel<CPL, L><<<tasks, 32, chunk_smem, stream>>>(p2);
+    const bool lg = a.logits != nullptr;  // raw-logit mode: one input tensor, one gradient tensor
+    if (stages >= 1) {
+        if (lg) tp_build_kernel<CPL, L, true><<<tasks, 32, chunk_smem, stream>>>(p2);
+        else tp_build_kernel<CPL, L, false><<<tasks, 32, chunk_smem, stream>>>(p2);
+    }
     SSNT_CUDA(cudaGetLastError());
     // dependent launches: each kernel's CTAs start while its predecessor drains and block in griddepcontrol.wait
     cudaLaunchAttribute pdl[1];
@@ -426,42 +432,9 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.gridDim = dim3(tasks);
         cfg.blockDim = dim3(32);
         cfg.dynamicSmemBytes = chunk_smem;
-        SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L>, pg));
+        if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, true>, pg));
+        else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, false>, pg));
     }
-}
-
-// Register-sweep time-parallel path (kind 8): group operators, boundary vectors, group interiors.
-template <int CPL>
-void launch_tp4(const TpParams& p, cudaStream_t stream) {
-    const FbArgs& a = p.a;
-    const size_t chunk_smem = 128 + (size_t)2 * kTp4Rows * a.max_u * sizeof(float);
-    const size_t ring_smem = 128 + (size_t)Tp4Dims<CPL>::NS * Tp4Dims<CPL>::stage_floats * sizeof(float);
-    static bool configured_[64] = {};  // per device
-    bool& configured = configured_[device_ordinal()];
-    if (!configured) {
-        SSNT_CUDA(cudaFuncSetAttribute(tp4_sweep_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
-        configured = true;
-    }
-    const unsigned tasks = (unsigned)a.batch_size * (unsigned)((a.max_t + kTp4Rows - 1) / kTp4Rows);
-    tp4_build_kernel<CPL><<<tasks, 32, chunk_smem, stream>>>(p);
-    SSNT_CUDA(cudaGetLastError());
-    cudaLaunchAttribute pdl[1];
-    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t cfg{};
-    cfg.stream = stream;
-    cfg.attrs = pdl;
-    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 7; }();  // tuning aid: 1 sweep, 2 fill, 4 re-run
-    cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
-    cfg.gridDim = dim3((unsigned)a.batch_size * 2u);
-    cfg.blockDim = dim3(32);
-    cfg.dynamicSmemBytes = ring_smem;
-    SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp4_sweep_kernel<CPL>, p));
-    cfg.numAttrs = (pdl_mask & 2) ? 1 : 0;
-    cfg.gridDim = dim3(tasks);
-    cfg.blockDim = dim3(32);
-    cfg.dynamicSmemBytes = chunk_smem;
-    SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp4_fill_kernel<CPL>, p));
 }
 
 }  // namespace
@@ -483,28 +456,6 @@ static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
     const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
     l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
     l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
-    l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
-              (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
-    return true;
-}
-
-// Register-sweep time-parallel path (kind 8): region 0 holds the group operators Q [B][NG][5][UP+4] (re-used as the
-// scratch rows of the log-domain re-run), then the boundary vectors A, Bv [B][NG+1][UP+32], the likelihood estimates
-// and the status words.
-struct Tp4Layout {
-    int CPL, UP, NG, SU;
-    size_t region0, vec, total;
-};
-static bool tp4_layout(int B, int max_t, int max_u, Tp4Layout& l) {
-    if (max_u % 4 != 0 || max_u > 256 || max_u <= 0 || max_t <= 0 || B <= 0) return false;
-    l.CPL = max_u <= 128 ? 4 : 8;
-    l.UP = 32 * l.CPL;
-    l.NG = (max_t + kTp4L - 1) / kTp4L;
-    l.SU = max_u + 32;
-    const size_t q = (size_t)B * l.NG * (kTp4L + 1) * (l.UP + 4) * sizeof(float);
-    const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
-    l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
-    l.vec = (((size_t)B * (l.NG + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
     l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
               (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
     return true;
@@ -532,8 +483,6 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     n = n > split_bytes ? n : split_bytes;
     TpLayout tl;
     if (tp_layout(B, max_t, max_u, tl)) n = n > tl.total ? n : tl.total;
-    Tp4Layout t4;
-    if (tp4_layout(B, max_t, max_u, t4)) n = n > t4.total ? n : t4.total;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -541,6 +490,59 @@ int fb_last_kernel_kind() { return tls_last_kind; }
 void fb_set_stats_buffer(long long* dev) { tls_stats = dev; }
 long long* fb_get_stats_buffer() { return tls_stats; }
 void fb_force_kernel_kind(int kind) { tls_force_kind = kind; }
+
+// ---- raw logits on shapes the fused kernels do not take ---------------------------------------------------------
+namespace {
+__global__ void logits_to_logprobs_kernel(const float* __restrict__ z, float* __restrict__ le, float* __restrict__ ls, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = z[i], sp = log1pf(expf(-fabsf(v)));
+        le[i] = fminf(v, 0.0f) - sp;   // log sigmoid(z)
+        ls[i] = fminf(-v, 0.0f) - sp;  // log sigmoid(-z)
+    }
+}
+__global__ void chain_logit_gradient_kernel(const float* __restrict__ z, const float* __restrict__ ge, const float* __restrict__ gs,
+                                            float* __restrict__ gz, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = z[i], t = expf(-fabsf(v)), r = 1.0f / (1.0f + t);
+        const float p = v >= 0.0f ? r : t * r, q = v >= 0.0f ? t * r : r;  // sigmoid(z), sigmoid(-z)
+        gz[i] = ge[i] * q - gs[i] * p;
+    }
+}
+}  // namespace
+
+static size_t logits_unfused_bytes(int B, int max_t, int max_u) {
+    return (((size_t)4 * B * max_t * max_u * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+size_t fb_logits_workspace_bytes(int B, int max_t, int max_u) {
+    if (B <= 0 || max_t <= 0 || max_u <= 0) return 256;
+    size_t n = fb_workspace_bytes(B, max_t, max_u);
+    if (max_u % 4 != 0 || max_u > 1024) n += logits_unfused_bytes(B, max_t, max_u);
+    return n;
+}
+
+void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream);
+static void launch_logits_unfused(const FbArgs& a, void* ws, cudaStream_t stream) {
+    const size_t n = (size_t)a.batch_size * a.max_t * a.max_u;
+    const size_t base = fb_workspace_bytes(a.batch_size, a.max_t, a.max_u);
+    float* tail;
+    if (a.workspace && a.workspace_bytes >= base + logits_unfused_bytes(a.batch_size, a.max_t, a.max_u)) {
+        tail = (float*)((char*)ws + base);
+    } else {  // e.g. an aligned shape with unaligned buffers: the query did not reserve the tail
+        tail = (float*)device_scratch(2, 4 * n * sizeof(float) + 16);
+    }
+    float *le = tail, *ls = tail + n, *ge = tail + 2 * n, *gs = tail + 3 * n;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 16);
+    logits_to_logprobs_kernel<<<blocks, 256, 0, stream>>>(a.logits, le, ls, n);
+    SSNT_CUDA(cudaGetLastError());
+    FbArgs b = a;
+    b.logits = nullptr; b.grad_logits = nullptr;
+    b.log_emit = le; b.log_shift = ls; b.grad_emit = ge; b.grad_shift = gs;
+    b.workspace = ws; b.workspace_bytes = base;
+    launch_forward_backward(b, stream);
+    chain_logit_gradient_kernel<<<blocks, 256, 0, stream>>>(a.logits, ge, gs, a.grad_logits, n);
+    SSNT_CUDA(cudaGetLastError());
+}
 
 void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     FbArgs a = a_in;
@@ -568,15 +570,24 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     unsigned* counter = done_counter_for(ws);
 
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    bool warp_ok = (a.max_u % 4 == 0) && a.max_u <= 1024 && aligned16(a.log_emit) &&
-                   aligned16(a.log_shift) && aligned16(a.grad_emit) && aligned16(a.grad_shift) &&
-                   aligned16(ws);
+    bool warp_ok = (a.max_u % 4 == 0) && a.max_u <= 1024 && aligned16(ws) &&
+                   (a.logits ? aligned16(a.logits) && aligned16(a.grad_logits)
+                             : aligned16(a.log_emit) && aligned16(a.log_shift) && aligned16(a.grad_emit) && aligned16(a.grad_shift));
+    if (a.logits && !warp_ok) {
+        // Raw logits on a shape the fused kernels do not take (max_u not a multiple of 4, > 1024, unaligned buffers):
+        // form the log-probabilities, run the ordinary path, chain the gradient — through the tail of the workspace.
+        launch_logits_unfused(a, ws, stream);
+        return;
+    }
     const bool bf_ok = warp_ok && a.max_u <= 256;
     const bool split_ok = bf_ok && (a.max_u == 64 || a.max_u == 128 || a.max_u == 256);
     int kind = tls_force_kind;
     // the time-parallel kernels (kind 6) win at every batch size measured (B = 4 .. 512, U = 64 / 128 / 256); the
     // single-kernel block-float paths (2: fused, 4: split-role) remain selectable
     if (kind < 0) kind = bf_ok ? 6 : (warp_ok ? 1 : 0);
+    if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
+        if (kind != 1 && kind != 6 && kind != 7) kind = bf_ok ? 6 : 1;
+    }
     if (kind == 6 || kind == 7) {
         TpLayout tl;
         SSNT_ASSERT(bf_ok && tp_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: time-parallel kernels forced on an unsupported shape");
@@ -626,46 +637,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         else launch_warp<8>(lp, smem, stream, pdl4);
         return;
     }
-    if (kind == 8 || kind == 9) {
-        Tp4Layout tl;
-        SSNT_ASSERT(bf_ok && tp4_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: register-sweep kernels forced on an unsupported shape");
-        tls_last_kind = kind;
-        TpParams p;
-        p.a = a;
-        char* base = (char*)ws;
-        p.Q = (float*)base;
-        p.A = (float*)(base + tl.region0);
-        p.Bv = (float*)(base + tl.region0 + tl.vec);
-        p.zlg = (float*)(base + tl.region0 + 2 * tl.vec);
-        p.status = (unsigned*)(base + tl.region0 + 2 * tl.vec + (((size_t)a.batch_size * 4 * sizeof(float) + 255) & ~(size_t)255));
-        p.C = tl.NG;
-        p.UP = tl.UP;
-        p.NS = 0;
-        p.G = tl.CPL;
-        p.debug = 0;
-        p.force_fallback = kind == 9 ? 1 : 0;  // kind 9: run the kernels but force the log-domain re-run
-        if (tl.CPL == 4) launch_tp4<4>(p, stream);
-        else launch_tp4<8>(p, stream);
-        // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
-        LogParams lp;
-        lp.a = a;
-        lp.scratch = (float*)ws;
-        lp.SU = tl.SU;
-        lp.counter = counter;
-        lp.only = p.status;
-        lp.fallbacks = device_fallback_counter();
-        const size_t stage_bytes = (size_t)kG * (2 * a.max_u + lp.SU) * sizeof(float);
-        const bool latency_mode = (size_t)a.batch_size * 2 <= (size_t)sm_count();
-        int LNS = (int)((latency_mode ? 192 * 1024 : 52 * 1024) / stage_bytes);
-        lp.NS = LNS < 2 ? 2 : (LNS > 8 ? 8 : LNS);
-        const size_t smem = 128 + (size_t)lp.NS * stage_bytes;
-        static const bool pdl4 = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? (std::atoi(e) & 4) != 0 : true; }();
-        const int lcpl = a.max_u <= 64 ? 2 : (a.max_u <= 128 ? 4 : 8);
-        if (lcpl == 2) launch_warp<2>(lp, smem, stream, pdl4);
-        else if (lcpl == 4) launch_warp<4>(lp, smem, stream, pdl4);
-        else launch_warp<8>(lp, smem, stream, pdl4);
-        return;
-    }
+    SSNT_ASSERT(kind <= 7, "forward_backward: unknown kernel kind (0 .. 7)");
     if (kind >= 4) SSNT_ASSERT(split_ok && a.batch_size <= 64, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");

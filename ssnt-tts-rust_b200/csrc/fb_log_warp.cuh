@@ -44,10 +44,12 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
     const FbArgs& a = p.a;
     const int max_t = a.max_t, max_u = a.max_u, SU = p.SU, NS = p.NS;
     const size_t slab = (size_t)max_t * max_u;
-    const float* le = a.log_emit + (size_t)b * slab;
-    const float* ls = a.log_shift + (size_t)b * slab;
-    float* ge = a.grad_emit + (size_t)b * slab;
-    float* gs = a.grad_shift + (size_t)b * slab;
+    // raw-logit mode (FbArgs::logits): one input tensor z and one gradient tensor; log2 sigmoid(+-z) formed per row
+    const bool logits = a.logits != nullptr;
+    const float* le = (logits ? a.logits : a.log_emit) + (size_t)b * slab;
+    const float* ls = logits ? nullptr : a.log_shift + (size_t)b * slab;
+    float* ge = (logits ? a.grad_logits : a.grad_emit) + (size_t)b * slab;
+    float* gs = logits ? nullptr : a.grad_shift + (size_t)b * slab;
     float* scr = p.scratch + (size_t)b * (max_t + 1) * SU;
     const int c0 = lane * CPL;
     const int UP = SU - 32;  // where the lane offsets start in a scratch row
@@ -73,9 +75,9 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
         float* dst = ring + (size_t)slot * stage_floats;
         const uint32_t bytes_e = (uint32_t)cnt * (uint32_t)max_u * 4u;
         const uint32_t bytes_x = with_x ? (uint32_t)cnt * (uint32_t)SU * 4u : 0u;
-        mbar_expect_tx(bar, 2u * bytes_e + bytes_x);
+        mbar_expect_tx(bar, (logits ? 1u : 2u) * bytes_e + bytes_x);
         bulk_g2s(smem_u32(dst + off_e), le + (size_t)r0 * max_u, bytes_e, bar);
-        bulk_g2s(smem_u32(dst + off_s), ls + (size_t)r0 * max_u, bytes_e, bar);
+        if (!logits) bulk_g2s(smem_u32(dst + off_s), ls + (size_t)r0 * max_u, bytes_e, bar);
         if (with_x) bulk_g2s(smem_u32(dst + off_x), scr + (size_t)(r0 + xoff) * SU, bytes_x, bar);
     };
 
@@ -90,6 +92,26 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
     auto convert = [&](float (&x)[CPL], bool all_masked) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) x[i] = (c0 + i < U && !all_masked) ? to_log2(x[i]) : kNeg;
+    };
+    // One row's log2 emit / shift scores from the ring stage.  Raw-logit mode: z' = z log2 e,
+    // log2 sigmoid(z) = min(z', 0) - log2(1 + 2^-|z'|), log2 sigmoid(-z) = that - z'; Zr keeps z' for the gradient.
+    auto load_row = [&](const float* st, int idx, int t, float (&E)[CPL], float (&Sh)[CPL], float (&Zr)[CPL]) {
+        load_cells<CPL>(st + off_e + idx * max_u, c0, max_u, 0.0f, E);
+        if (logits) {
+            const bool last = t == T - 1;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const float zz = fminf(fmaxf(E[i] * kLog2e, kNeg), -kNeg);
+                const float sp = lg2(1.0f + ex2(-fabsf(zz)));
+                Zr[i] = zz;
+                E[i] = (c0 + i < U) ? fmaxf(fminf(zz, 0.0f) - sp, kNeg) : kNeg;
+                Sh[i] = (c0 + i < U && !last) ? fmaxf(fminf(-zz, 0.0f) - sp, kNeg) : kNeg;
+            }
+        } else {
+            load_cells<CPL>(st + off_s + idx * max_u, c0, max_u, 0.0f, Sh);
+            convert(E, false);
+            convert(Sh, t == T - 1);  // the last frame must emit
+        }
     };
     auto lane_max = [&]() {
         float mx = v[0];
@@ -161,11 +183,8 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
                 if (q < cnt) {
                     const int t = t0 + dir * (j0 + q);
                     const int idx = dir > 0 ? q : cnt - 1 - q;
-                    float E[CPL], Sh[CPL];
-                    load_cells<CPL>(st + off_e + idx * max_u, c0, max_u, 0.0f, E);
-                    load_cells<CPL>(st + off_s + idx * max_u, c0, max_u, 0.0f, Sh);
-                    convert(E, false);
-                    convert(Sh, t == T - 1);  // the last frame must emit
+                    float E[CPL], Sh[CPL], Zr[CPL];
+                    load_row(st, idx, t, E, Sh, Zr);
                     if (rank == 0) {
                         alpha_step(E, Sh);
                         store_state_row(t + 1);
@@ -221,14 +240,11 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
                 if (q < cnt) {
                     const int t = t0 + dir * (j0 + q);
                     const int idx = dir > 0 ? q : cnt - 1 - q;
-                    float E[CPL], Sh[CPL], X[CPL];
-                    load_cells<CPL>(st + off_e + idx * max_u, c0, max_u, 0.0f, E);
-                    load_cells<CPL>(st + off_s + idx * max_u, c0, max_u, 0.0f, Sh);
+                    float E[CPL], Sh[CPL], X[CPL], Zr[CPL];
+                    load_row(st, idx, t, E, Sh, Zr);
                     const float* xrow = st + off_x + idx * SU;
                     load_cells<CPL>(xrow, c0, max_u, kNeg, X);
                     const float xo = xrow[UP + lane];  // partner's lane offset of that row
-                    convert(E, false);
-                    convert(Sh, t == T - 1);
                     const bool first = (j0 + q) == 0;  // t == m-1: the meeting row
                     // beta~(t+1,u) in frame fb, and its right neighbour brought into the same frame
                     float bn[CPL], x[CPL], y[CPL];
@@ -287,8 +303,17 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
                             g1[i] = dead ? 0.0f : ex2((av + x[i]) + kt);
                             g2[i] = dead ? 0.0f : ex2((av + y[i]) + kt);
                         }
-                        store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
-                        store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+                        if (logits) {  // dLL/dz = occupancy(emit) sigmoid(-z) - occupancy(shift) sigmoid(z)
+#pragma unroll
+                            for (int i = 0; i < CPL; ++i) {
+                                const float sp = lg2(1.0f + ex2(-fabsf(Zr[i])));
+                                g1[i] = g1[i] * ex2(fminf(-Zr[i], 0.0f) - sp) - g2[i] * ex2(fminf(Zr[i], 0.0f) - sp);
+                            }
+                            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
+                        } else {
+                            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
+                            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+                        }
                     }
                     if (rank == 0) {
                         if (t < T - 1) alpha_step(E, Sh);
@@ -307,7 +332,7 @@ __device__ void log_lattice_cta(const LogParams& p, int b, unsigned rank, int la
     {
         const float zeros[CPL] = {};
         float* g = rank == 0 ? ge : gs;
-        for (int t = T; t < max_t; ++t) store_cells_cs<CPL>(g + (size_t)t * max_u, c0, max_u, zeros);
+        if (g) for (int t = T; t < max_t; ++t) store_cells_cs<CPL>(g + (size_t)t * max_u, c0, max_u, zeros);
     }
 }
 

@@ -123,10 +123,47 @@ __device__ __forceinline__ void tp_row_probs(const float* se, const float* ss, i
     }
 }
 
-// Starts the two bulk copies of a chunk's raw rows (lane 0 only) and returns after arming the barrier.
+// sigmoid(z) and sigmoid(-z) from one EX2 and one RCP, both to full relative accuracy:
+// t = 2^-|z'|, r = 1 / (1 + t):  sigmoid(|z|) = r, sigmoid(-|z|) = t r.
+__device__ __forceinline__ void sigmoid_pair(float z, float& p, float& q) {
+    const float zz = z * kLog2e;
+    const float t = ex2(-fabsf(zz));
+    const float r = __frcp_rn(1.0f + t);
+    const float tr = t * r;
+    p = zz >= 0.0f ? r : tr;
+    q = zz >= 0.0f ? tr : r;
+}
+
+// Raw-logit mode: one lattice row as probabilities from the logit row in shared memory; (e, s) carry the lattice's
+// masks like tp_row_probs, (pu, qu) are the unmasked sigmoid(z), sigmoid(-z) the gradient is chained through.
+template <int CPL>
+__device__ __forceinline__ void tp_row_probs_logits(const float* sz, int l, int t, int T, int U, int max_u, int c0,
+                                                    float (&e)[CPL], float (&s)[CPL], float (&pu)[CPL], float (&qu)[CPL]) {
+    if (t < T) {
+        float rz[CPL];
+        load_cells<CPL>(sz + l * max_u, c0, max_u, 0.0f, rz);
+        const bool last = t == T - 1;
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            sigmoid_pair(rz[r], pu[r], qu[r]);
+            e[r] = (c0 + r < U) ? pu[r] : 0.0f;
+            s[r] = (c0 + r < U - 1 && !last) ? qu[r] : 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) { e[r] = 1.0f; s[r] = 0.0f; pu[r] = 0.0f; qu[r] = 0.0f; }
+    }
+}
+
+// Starts the bulk copies of a chunk's raw rows (lane 0 only) and returns after arming the barrier.
 __device__ __forceinline__ void tp_issue_chunk(const FbArgs& a, int b, int t0, int rows, float* se, float* ss, uint32_t bar) {
     const size_t slab = (size_t)a.max_t * a.max_u;
     const uint32_t bytes = (uint32_t)rows * (uint32_t)a.max_u * 4u;
+    if (a.logits) {  // raw-logit mode: one tensor
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(se), a.logits + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
+        return;
+    }
     mbar_expect_tx(bar, 2u * bytes);
     bulk_g2s(smem_u32(se), a.log_emit + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
     bulk_g2s(smem_u32(ss), a.log_shift + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
@@ -143,7 +180,7 @@ __device__ __forceinline__ bool tp_lengths(const FbArgs& a, int b, int& T, int& 
 // =================================================================================================
 // Kernel 1: chunk operators.
 // =================================================================================================
-template <int CPL, int L>
+template <int CPL, int L, bool LG = false>
 __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FbArgs& a = p.a;
@@ -178,7 +215,12 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         float e[CPL], s[CPL];
-        tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+        if constexpr (LG) {
+            float pu[CPL], qu[CPL];
+            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+        } else {
+            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+        }
         // what enters this lane's first token from the left neighbour's last token, per diagonal
         float X[L];
 #pragma unroll
@@ -408,7 +450,7 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
 // =================================================================================================
 // Kernel 3: chunk interiors and gradients.
 // =================================================================================================
-template <int CPL, int L>
+template <int CPL, int L, bool LG = false>
 __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FbArgs& a = p.a;
@@ -418,13 +460,13 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     const int c0 = lane * CPL;
     const int t0 = c * L;
     const size_t slab = (size_t)max_t * max_u;
-    float* ge = a.grad_emit + (size_t)b * slab;
-    float* gs = a.grad_shift + (size_t)b * slab;
+    float* ge = (LG ? a.grad_logits : a.grad_emit) + (size_t)b * slab;   // raw-logit mode: the one gradient tensor
+    float* gs = LG ? nullptr : a.grad_shift + (size_t)b * slab;
     const float zeros[CPL] = {};
     auto zero_rows = [&](int from, int to) {
         for (int t = from; t < to; ++t) {
             store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            if constexpr (!LG) store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
         }
     };
     int T, U;
@@ -535,9 +577,14 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         float e[CPL], s[CPL];
-        tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
-        store_cells<CPL>(se + l * max_u, c0, max_u, e);  // the raw rows are overwritten in place by the probabilities
-        store_cells<CPL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
+        if constexpr (LG) {  // the logit rows stay in place: the beta sweep converts them again (it needs the unmasked pair)
+            float pu[CPL], qu[CPL];
+            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+        } else {
+            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+            store_cells<CPL>(se + l * max_u, c0, max_u, e);  // the raw rows are overwritten in place by the probabilities
+            store_cells<CPL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
+        }
 #pragma unroll
         for (int r = 0; r < CPL; ++r) ar[l][r] = av[r] * sa;
         if (l < L - 1) {
@@ -553,9 +600,13 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #pragma unroll
     for (int l = L - 1; l >= 0; --l) {
         const int t = t0 + l;
-        float e[CPL], s[CPL];
-        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
-        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+        float e[CPL], s[CPL], pu[CPL], qu[CPL];
+        if constexpr (LG) {
+            tp_row_probs_logits<CPL>(se, l, t, T, U, max_u, c0, e, s, pu, qu);
+        } else {
+            load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
+            load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+        }
         const float bin = __shfl_down_sync(kFull, bv[0], 1) * kb;
         float g1[CPL], g2[CPL];
         float rowsum = 0.0f;
@@ -569,8 +620,15 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
             bv[r] = p1 + p2;
         }
         if (t < T) {
-            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
-            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+            if constexpr (LG) {  // dLL/dz = occupancy(emit) sigmoid(-z) - occupancy(shift) sigmoid(z)
+                float gz[CPL];
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) gz[r] = g1[r] * qu[r] - g2[r] * pu[r];
+                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, gz);
+            } else {
+                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
+                store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+            }
             rowsum = warp_sum(rowsum);
             const float dev = fabsf(rowsum - 1.0f);
             worst = (dev <= kTpRowTol) ? worst : 1.0f;  // also catches NaN
@@ -579,7 +637,7 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #endif
         } else if (t < max_t) {
             store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            if constexpr (!LG) store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
         }
     }
     if (worst != 0.0f && lane == 0) atomicOr(p.status + b, (unsigned)kTpBadRow);

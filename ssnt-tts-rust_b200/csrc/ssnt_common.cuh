@@ -123,8 +123,14 @@ struct FbArgs {
     void* workspace;
     size_t workspace_bytes;
     struct LossExchange* xchg = nullptr;  // set by the launcher when a loss exchange is connected (multi-GPU)
+    // Raw-logit mode (ssnt_tts_forward_backward_logits): log_emit = log sigmoid(z), log_shift = log sigmoid(-z) are
+    // formed on the fly and the gradient is chained through them, dLL/dz = grad_emit * sigmoid(-z) - grad_shift * sigmoid(z).
+    // When `logits` is set, log_emit / log_shift / grad_emit / grad_shift are null.
+    const float* logits = nullptr;   // [B,T,U]
+    float* grad_logits = nullptr;    // [B,T,U]
 };
 size_t fb_workspace_bytes(int batch_size, int max_t, int max_u);
+size_t fb_logits_workspace_bytes(int batch_size, int max_t, int max_u);  // raw-logit mode (adds the unfused path's buffers where needed)
 void launch_forward_backward(const FbArgs& a, cudaStream_t stream);
 // Which kernel family the last launch_forward_backward on this thread used (1 = warp/TMA
 // lattice kernel, 0 = generic block kernel); for tests and the bench's launch accounting.

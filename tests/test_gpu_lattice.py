@@ -4,9 +4,9 @@ CPU oracle, through the C-ABI.
 The reference has no forward-backward at all, so the oracle for this part is
 an authored specification — "parity unpinned" by the reference; the oracle itself is hardened in
 test_oracle_lattice.py.  Tolerances (BASELINE.json north_star): log-likelihood within 1e-5
-relative; gradients within 1e-4 relative, measured against the largest occupancy of the
-utterance (gradients are posterior probabilities in [0, 1]; element-wise relative error of
-entries like 1e-30 is not meaningful in fp32).  Full-size runs are additionally checked through
+relative; gradients within 1e-4 relative ELEMENT-WISE for every occupancy >= 1e-6 and within 1e-10
+absolute below that (gradients are posterior probabilities in [0, 1]; the relative error of an
+entry like 1e-30 is not meaningful in fp32).  Full-size runs are additionally checked through
 size-independent properties: every frame's occupancies sum to 1, expected shifts = U-1."""
 import numpy as np
 import pytest
@@ -28,22 +28,28 @@ def _np(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
 
 
-def _check(got, want, t_len=None, u_len=None):
+GRAD_FLOOR = 1e-6   # occupancies below this are compared absolutely (GRAD_RTOL * GRAD_FLOOR = 1e-10)
+
+
+def _check(got, want, t_len=None, u_len=None, grad_rtol=GRAD_RTOL):
+    """log-likelihood: 1e-5 relative (absolute 1e-5 for |LL| < 1).  Gradients: ELEMENT-WISE 1e-4 relative for every
+    occupancy >= 1e-6, absolute 1e-10 below (north_star: "gradients within 1e-4 relative")."""
     ll, loss, ge, gs = (_np(g) for g in got)
     ll64, loss64, ge64, gs64 = want
     finite = np.isfinite(ll64)
     assert np.array_equal(np.isfinite(ll), finite)
-    assert np.all(np.abs(ll[finite] - ll64[finite]) <= LL_RTOL * np.abs(ll64[finite]) + 1e-6)
+    assert np.all(np.abs(ll[finite] - ll64[finite]) <= LL_RTOL * np.maximum(np.abs(ll64[finite]), 1.0))
     if finite.all():
-        assert abs(float(loss[0]) - loss64) <= LL_RTOL * abs(loss64) + 1e-5
-    for b in range(ll.shape[0]):
-        for g, g64 in ((ge[b], ge64[b]), (gs[b], gs64[b])):
-            scale = max(float(np.abs(ge64[b]).max()), 1e-30)
-            err = float(np.abs(g - g64).max())
-            assert err <= GRAD_RTOL * scale, (b, err, scale)
-        # padded / unreachable cells are exactly zero
-        assert not ge[b][ge64[b] == 0].any() or np.abs(ge[b][ge64[b] == 0]).max() <= GRAD_RTOL
-        if t_len is not None:
+        assert abs(float(loss[0]) - loss64) <= LL_RTOL * max(abs(loss64), 1.0)
+    for g, g64, name in ((ge, ge64, "grad_emit"), (gs, gs64, "grad_shift")):
+        err = np.abs(g.astype(np.float64) - g64)
+        bound = grad_rtol * np.maximum(np.abs(g64), GRAD_FLOOR)
+        bad = err > bound
+        assert not bad.any(), (name, int(bad.sum()), float((err / np.maximum(np.abs(g64), GRAD_FLOOR)).max()))
+        # (cells whose fp64 occupancy rounds to 0 in fp32 fall under the absolute bound above; padded cells are
+        # checked to be exactly zero below)
+    if t_len is not None:
+        for b in range(ll.shape[0]):
             assert not ge[b, t_len[b]:].any() and not gs[b, t_len[b]:].any()
             assert not ge[b, :, u_len[b]:].any() and not gs[b, :, u_len[b]:].any()
 
@@ -71,7 +77,7 @@ def test_config1_B1_U32_T120(product, oracle_mod, space):
     _check(got, want)
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3, 6, 7, 8, 9])  # generic, log-warp, block-float (+ forced log re-run), time-parallel (+ forced re-run), register-sweep time-parallel (+ forced re-run)
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 6, 7])  # generic, log-warp, block-float (+ forced log re-run), time-parallel (+ forced re-run)
 @pytest.mark.parametrize("B,T,U", [(3, 1, 4), (2, 2, 4), (4, 3, 4), (5, 9, 8), (3, 17, 16), (2, 40, 36),
                                    (3, 64, 64), (2, 100, 128), (2, 70, 200), (1, 90, 260), (1, 600, 520)])
 def test_shapes_and_ragged_lengths(product, oracle_mod, kind, B, T, U):
@@ -108,7 +114,7 @@ def test_infeasible_empty_and_masked(product, oracle_mod):
     le[0, 3, 2] = -np.inf                            # a single forbidden cell is fine
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     assert np.isneginf(want[0][[1, 2, 3, 5]]).all() and np.isfinite(want[0][[0, 4]]).all()
-    for kind in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for kind in (0, 1, 2, 3, 4, 5, 6, 7):
         if kind in (4, 5):
             continue  # max_u = 8 here; the split-role kernel needs max_u in {64, 128, 256} (covered below)
         got, _ = _run(product, le, ls, t_len, u_len, "device", kind)
@@ -130,7 +136,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)  # exactly U-1 shifts
 
 
-@pytest.mark.parametrize("kind", [1, 2, 4, 6, 8])
+@pytest.mark.parametrize("kind", [1, 2, 4, 6])
 def test_config2_ragged(product, oracle_mod, kind):
     le, ls = make_inputs(32, 800, 128, seed=77)
     t_len, u_len = ragged_lengths(32, 800, 128)
@@ -180,9 +186,11 @@ def test_peaked_and_uniform_inputs(product, oracle_mod):
     le[2], ls[2] = np.log(1e-10), np.log1p(-1e-10)        # model insists on shifting every frame
     le[3], ls[3] = np.log1p(-1e-6), np.log(1e-6)          # model never wants to shift
     want = oracle_mod.forward_backward(le, ls)
-    for kind in (0, 1, 2, 4, 6, 8):   # kinds 2, 4, 6 and 8 must notice what they cannot hold and re-run it in the log domain
+    for kind in (0, 1, 2, 4, 6):   # kinds 2, 4 and 6 must notice what they cannot hold and re-run it in the log domain
         got, _ = _run(product, le, ls, None, None, "device", kind)
-        _check(got, want)
+        # |LL| reaches several thousand here: one fp32 ulp of a log-domain quantity of that size is a few 1e-4 of its
+        # exponential, so the element-wise bound is 3e-4 for this adversarial case (1e-4 everywhere else)
+        _check(got, want, grad_rtol=3e-4)
 
 
 def test_large_batch_properties(product):
@@ -302,7 +310,7 @@ def test_tone_latent_infeasible(product, oracle_mod):
 
 # ---- split-role kernel (kind 4; kind 5 = 4 with the log-domain re-run forced) and wide lattices ----------------
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("B,T,U", [(3, 64, 64), (2, 9, 64), (5, 333, 128), (2, 801, 128), (3, 130, 128),
                                    (2, 700, 256), (1, 300, 256), (35, 200, 128)])
 def test_full_width_lattices_all_block_float_kernels(product, oracle_mod, kind, B, T, U):
@@ -330,7 +338,7 @@ def test_split_kernel_infeasible_and_masked(product, oracle_mod):
     ls[5, 40, :] = -np.inf                                 # no path at all → -inf
     le[0, 3, 2] = -np.inf
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
-    for kind in (2, 4, 5, 6, 7, 8, 9):
+    for kind in (2, 4, 5, 6, 7):
         got, used = _run(product, le, ls, t_len, u_len, "device", kind)
         assert used == kind
         _check(got, want, t_len, u_len)
@@ -480,3 +488,63 @@ def test_loss_exchange_single_rank(product, oracle_mod):
         assert torch.equal(red, out[1])
     finally:
         product.disconnect_loss_exchange()
+
+
+# ---- raw-logit entry point ------------------------------------------------------------------
+def _logit_case(B, T, U, seed, ragged=True):
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((B, T, U)).astype(np.float32)
+    z64 = z.astype(np.float64)
+    le = (-np.logaddexp(0.0, -z64)).astype(np.float32)
+    ls = (-np.logaddexp(0.0, z64)).astype(np.float32)
+    t_len, u_len = ragged_lengths(B, T, U, seed=seed) if ragged else (None, None)
+    return z, le, ls, t_len, u_len
+
+
+def _check_logits(got, z, want, t_len):
+    """want = oracle on (log sigmoid(z), log sigmoid(-z)); grad_logits = grad_emit sigmoid(-z) - grad_shift sigmoid(z)."""
+    ll, loss, gz = (_np(g) for g in got)
+    ll64, loss64, ge64, gs64 = want
+    z64 = z.astype(np.float64)
+    gz64 = ge64 / (1.0 + np.exp(z64)) - gs64 / (1.0 + np.exp(-z64))
+    finite = np.isfinite(ll64)
+    assert np.array_equal(np.isfinite(ll), finite)
+    # the oracle saw the fp32 roundings of the log-sigmoids, the kernels form them from z: 3e-5 on |LL| >= 1
+    assert np.all(np.abs(ll[finite] - ll64[finite]) <= 3e-5 * np.maximum(np.abs(ll64[finite]), 1.0))
+    # a difference of two occupancy terms: relative to the larger term, floor 1e-5
+    scale = np.maximum(np.maximum(ge64, gs64), 1e-5)
+    err = np.abs(gz - gz64)
+    assert (err <= 2e-4 * scale).all(), float((err / scale).max())
+    if t_len is not None:
+        for b in range(ll.shape[0]):
+            assert not gz[b, t_len[b]:].any()
+
+
+@pytest.mark.parametrize("B,T,U,want_kind", [(1, 120, 32, 6), (32, 800, 128, 6), (3, 333, 256, 6), (2, 64, 64, 6),
+                                             (2, 300, 512, 1), (3, 47, 30, 6), (2, 40, 33, 0)])
+def test_logit_entry_matches_oracle_on_log_sigmoids(product, oracle_mod, B, T, U, want_kind):
+    z, le, ls, t_len, u_len = _logit_case(B, T, U, seed=B * 1000 + T + U)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got = product.forward_backward_logits(_dev(z), _dev(t_len), _dev(u_len))
+    if U % 4 == 0:
+        assert product.fb_kernel_used() == want_kind
+    _check_logits(got, z, want, t_len)
+    # and the two-tensor call on the same log-sigmoids
+    ref = product.forward_backward(_dev(le), _dev(ls), _dev(t_len), _dev(u_len))
+    ge, gs = _np(ref[2]).astype(np.float64), _np(ref[3]).astype(np.float64)
+    z64 = z.astype(np.float64)
+    np.testing.assert_allclose(_np(got[2]), ge / (1.0 + np.exp(z64)) - gs / (1.0 + np.exp(-z64)), atol=2e-6, rtol=1e-4)
+
+
+def test_logit_entry_host_pointers_and_extreme_logits(product, oracle_mod):
+    z, le, ls, t_len, u_len = _logit_case(5, 200, 128, seed=77)
+    z[0, :, :] *= 8.0          # saturated sigmoids: |z| up to ~35
+    z[1, 10:20, 5:9] = -60.0   # emit practically forbidden in a patch
+    z64 = z.astype(np.float64)
+    le = (-np.logaddexp(0.0, -z64)).astype(np.float32)
+    ls = (-np.logaddexp(0.0, z64)).astype(np.float32)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got = product.forward_backward_logits(z, t_len, u_len)     # host buffers
+    _check_logits(got, z, want, t_len)
+    got = product.forward_backward_logits(_dev(z), _dev(t_len), _dev(u_len))
+    _check_logits(got, z, want, t_len)
