@@ -361,6 +361,9 @@ def kernel_description(kind, K):
     return {6: "time-parallel block-float kernels: tp_build_kernel (chunk transfer operators, TMA-fed, one warp per 16-frame chunk) "
                "+ tp_combine_kernel (banded mat-vec sweep over the chunk boundaries, TMA ring, per-group exponents) "
                "+ tp_fill_kernel (chunk interiors and gradients) + fb_log_warp_kernel (re-run of flagged utterances only, loss)",
+            8: "warp-serial block-float kernels (large batches): ws_forward_kernel (one warp per utterance, alpha in registers, "
+               "rows through a TMA ring, a checkpoint every 8-16 rows) + ws_backward_kernel (chunks from the end: alpha re-run "
+               "from the checkpoint, beta and gradients fused) + fb_log_warp_kernel (re-run of flagged utterances only, loss)",
             4: "fb_split_kernel (block-float; cluster of 4 CTAs per utterance: 2 recursion CTAs + 2 gradient CTAs, "
                "rows by ld.global.cg + L2 prefetch, DSMEM flags)",
             2: "fb_bf_kernel (block-float, warp-specialised cluster of 2 CTAs, TMA ring)",
@@ -369,7 +372,7 @@ def kernel_description(kind, K):
 
 
 def launches_per_step(kind, K):
-    return 2 if K else {6: 4}.get(kind, 1)
+    return 2 if K else {6: 4, 8: 3}.get(kind, 1)
 
 
 def measure_lattice(P, dev, name, B, steps, warmup, world, rank, fb_kernel=-1, use_graph=True, exchange=False):
@@ -704,7 +707,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true", help="issue every step from Python instead of replaying CUDA graphs")
     ap.add_argument("--fb-kernel", type=int, default=-1,
-                    help="-1 auto, 0 generic, 1 log-warp, 2 block-float fused, 4 block-float split-role, 6 time-parallel block-float")
+                    help="-1 auto, 0 generic, 1 log-warp, 2 block-float fused, 4 block-float split-role, 6 time-parallel block-float, "
+                         "8 warp-serial block-float (large batches)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -161,7 +161,8 @@ class _Call:
 def set_fb_kernel(kind: int) -> None:
     """-1 auto, 0 generic block kernel, 1 log-domain warp/TMA cluster kernel, 2 block-float fused
     kernel, 4 block-float split-role kernel, 6 time-parallel block-float kernels (the default hot
-    path); 3 / 5 / 7 = 2 / 4 / 6 with the log-domain re-run forced (tests and benchmarks)."""
+    path), 8 warp-serial block-float kernels (the default for large batches); 3 / 5 / 7 / 9 = 2 / 4 / 6 / 8
+    with the log-domain re-run forced (tests and benchmarks)."""
     lib().ssnt_tts_set_fb_kernel(c_int(kind))
 
 

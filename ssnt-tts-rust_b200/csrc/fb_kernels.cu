@@ -15,6 +15,7 @@
 //            domain with one integer offset per token.
 #include "fb_split.cuh"
 #include "fb_tp.cuh"
+#include "fb_ws.cuh"
 
 namespace ssnt {
 namespace {
@@ -437,6 +438,34 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     }
 }
 
+// Warp-serial throughput path (kind 8): alpha checkpoints forward, chunked beta + gradients backward.
+template <int CPL, int L>
+void launch_ws(const WsParams& p, cudaStream_t stream) {
+    const FbArgs& a = p.a;
+    const size_t fwd_smem = 128 + (size_t)kWsFwdStages * 2 * p.R * a.max_u * sizeof(float);
+    const size_t bwd_smem = 128 + (size_t)2 * 2 * L * a.max_u * sizeof(float);
+    static bool configured_[64] = {};  // per device
+    bool& configured = configured_[device_ordinal()];
+    if (!configured) {
+        SSNT_CUDA(cudaFuncSetAttribute(ws_forward_kernel<CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SSNT_CUDA(cudaFuncSetAttribute(ws_backward_kernel<CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    ws_forward_kernel<CPL, L><<<(unsigned)a.batch_size, 32, fwd_smem, stream>>>(p);
+    SSNT_CUDA(cudaGetLastError());
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = stream;
+    cfg.attrs = pdl;
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)a.batch_size);
+    cfg.blockDim = dim3(32);
+    cfg.dynamicSmemBytes = bwd_smem;
+    SSNT_CUDA(cudaLaunchKernelEx(&cfg, ws_backward_kernel<CPL, L>, p));
+}
+
 }  // namespace
 
 // Time-parallel path (kind 6): region 0 holds the chunk operators Q [B][C][L+1][UP] and is re-used as the scratch
@@ -457,6 +486,28 @@ static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
     l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
     l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
     l.total = l.region0 + 2 * l.vec + (((size_t)B * 4 * sizeof(float) + 255) & ~(size_t)255) +
+              (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
+    return true;
+}
+
+// Warp-serial path (kind 8): region 0 = the scratch rows of the log-domain re-run; then the alpha checkpoints
+// A [B][C+1][UP+32], the forward likelihoods and the status words.
+struct WsLayout {
+    int CPL, L, UP, C, SU, R;
+    size_t region0, vec, total;
+};
+static bool ws_layout(int B, int max_t, int max_u, WsLayout& l) {
+    if (max_u % 4 != 0 || max_u > 256 || max_u <= 0 || max_t <= 0 || B <= 0) return false;
+    l.CPL = max_u <= 64 ? 2 : (max_u <= 128 ? 4 : 8);
+    l.L = l.CPL == 8 ? 8 : 16;
+    l.UP = 32 * l.CPL;
+    l.C = (max_t + l.L - 1) / l.L;
+    l.SU = max_u + 32;
+    l.R = (kWsStageBytes / (8 * max_u)) & ~3;  // whole groups of four rows
+    if (l.R < 4) l.R = 4;
+    l.region0 = (((size_t)B * (max_t + 1) * l.SU * sizeof(float)) + 255) & ~(size_t)255;
+    l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
+    l.total = l.region0 + l.vec + (((size_t)B * 2 * sizeof(float) + 255) & ~(size_t)255) +
               (((size_t)B * sizeof(unsigned) + 255) & ~(size_t)255);
     return true;
 }
@@ -483,6 +534,8 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     n = n > split_bytes ? n : split_bytes;
     TpLayout tl;
     if (tp_layout(B, max_t, max_u, tl)) n = n > tl.total ? n : tl.total;
+    WsLayout wl;
+    if (ws_layout(B, max_t, max_u, wl)) n = n > wl.total ? n : wl.total;
     return (n + 255) & ~(size_t)255;
 }
 
@@ -585,6 +638,13 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     // the time-parallel kernels (kind 6) win at every batch size measured (B = 4 .. 512, U = 64 / 128 / 256); the
     // single-kernel block-float paths (2: fused, 4: split-role) remain selectable
     if (kind < 0) kind = bf_ok ? 6 : (warp_ok ? 1 : 0);
+    // Large batches: the warp-serial kernels (kind 8) move 25 bytes per cell instead of ~37 and win once every SM holds
+    // enough utterances to hide one warp's row latency.  Measured on B200 (G cells/s, kind 6 vs 8), T=2000 U=256:
+    // B=512 135/135, 1024 137/166, 2048 138/186, 4096 140/213; T=800 U=128: B=1024 157/123, 2048 161/170, 4096 163/190.
+    if (tls_force_kind < 0 && kind == 6 && !a.logits) {
+        const size_t per_sm = (size_t)a.batch_size / (size_t)sm_count();
+        if ((a.max_u > 128 && per_sm >= 5) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 12)) kind = 8;
+    }
     if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
         if (kind != 1 && kind != 6 && kind != 7) kind = bf_ok ? 6 : 1;
     }
@@ -637,7 +697,42 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         else launch_warp<8>(lp, smem, stream, pdl4);
         return;
     }
-    SSNT_ASSERT(kind <= 7, "forward_backward: unknown kernel kind (0 .. 7)");
+    if (kind == 8 || kind == 9) {
+        WsLayout wl;
+        SSNT_ASSERT(bf_ok && ws_layout(a.batch_size, a.max_t, a.max_u, wl), "forward_backward: warp-serial kernels forced on an unsupported shape");
+        tls_last_kind = kind;
+        WsParams p;
+        p.a = a;
+        char* base = (char*)ws;
+        p.A = (float*)(base + wl.region0);
+        p.zlg = (float*)(base + wl.region0 + wl.vec);
+        p.status = (unsigned*)(base + wl.region0 + wl.vec + (((size_t)a.batch_size * 2 * sizeof(float) + 255) & ~(size_t)255));
+        p.C = wl.C;
+        p.UP = wl.UP;
+        p.R = wl.R;
+        p.force_fallback = kind == 9 ? 1 : 0;  // kind 9: run the kernels but force the log-domain re-run
+        if (wl.CPL == 2) launch_ws<2, 16>(p, stream);
+        else if (wl.CPL == 4) launch_ws<4, 16>(p, stream);
+        else launch_ws<8, 8>(p, stream);
+        // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
+        LogParams lp;
+        lp.a = a;
+        lp.scratch = (float*)ws;
+        lp.SU = wl.SU;
+        lp.counter = counter;
+        lp.only = p.status;
+        lp.fallbacks = device_fallback_counter();
+        const size_t stage_bytes = (size_t)kG * (2 * a.max_u + lp.SU) * sizeof(float);
+        const bool latency_mode = (size_t)a.batch_size * 2 <= (size_t)sm_count();
+        int LNS = (int)((latency_mode ? 192 * 1024 : 52 * 1024) / stage_bytes);
+        lp.NS = LNS < 2 ? 2 : (LNS > 8 ? 8 : LNS);
+        const size_t smem = 128 + (size_t)lp.NS * stage_bytes;
+        if (wl.CPL == 2) launch_warp<2>(lp, smem, stream, true);
+        else if (wl.CPL == 4) launch_warp<4>(lp, smem, stream, true);
+        else launch_warp<8>(lp, smem, stream, true);
+        return;
+    }
+    SSNT_ASSERT(kind <= 7, "forward_backward: unknown kernel kind (0 .. 9)");
     if (kind >= 4) SSNT_ASSERT(split_ok && a.batch_size <= 64, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");

@@ -77,7 +77,7 @@ def test_config1_B1_U32_T120(product, oracle_mod, space):
     _check(got, want)
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3, 6, 7])  # generic, log-warp, block-float (+ forced log re-run), time-parallel (+ forced re-run)
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 6, 7, 8, 9])  # generic, log-warp, block-float (+ forced log re-run), time-parallel (+ forced re-run), warp-serial (+ forced re-run)
 @pytest.mark.parametrize("B,T,U", [(3, 1, 4), (2, 2, 4), (4, 3, 4), (5, 9, 8), (3, 17, 16), (2, 40, 36),
                                    (3, 64, 64), (2, 100, 128), (2, 70, 200), (1, 90, 260), (1, 600, 520)])
 def test_shapes_and_ragged_lengths(product, oracle_mod, kind, B, T, U):
@@ -114,7 +114,7 @@ def test_infeasible_empty_and_masked(product, oracle_mod):
     le[0, 3, 2] = -np.inf                            # a single forbidden cell is fine
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
     assert np.isneginf(want[0][[1, 2, 3, 5]]).all() and np.isfinite(want[0][[0, 4]]).all()
-    for kind in (0, 1, 2, 3, 4, 5, 6, 7):
+    for kind in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9):
         if kind in (4, 5):
             continue  # max_u = 8 here; the split-role kernel needs max_u in {64, 128, 256} (covered below)
         got, _ = _run(product, le, ls, t_len, u_len, "device", kind)
@@ -136,7 +136,7 @@ def test_config2_B32_U128_T800(product, oracle_mod, space):
     np.testing.assert_allclose(gs.sum(axis=(1, 2)), 127.0, rtol=1e-4)  # exactly U-1 shifts
 
 
-@pytest.mark.parametrize("kind", [1, 2, 4, 6])
+@pytest.mark.parametrize("kind", [1, 2, 4, 6, 8])
 def test_config2_ragged(product, oracle_mod, kind):
     le, ls = make_inputs(32, 800, 128, seed=77)
     t_len, u_len = ragged_lengths(32, 800, 128)
@@ -186,7 +186,7 @@ def test_peaked_and_uniform_inputs(product, oracle_mod):
     le[2], ls[2] = np.log(1e-10), np.log1p(-1e-10)        # model insists on shifting every frame
     le[3], ls[3] = np.log1p(-1e-6), np.log(1e-6)          # model never wants to shift
     want = oracle_mod.forward_backward(le, ls)
-    for kind in (0, 1, 2, 4, 6):   # kinds 2, 4 and 6 must notice what they cannot hold and re-run it in the log domain
+    for kind in (0, 1, 2, 4, 6, 8):   # kinds 2, 4, 6 and 8 must notice what they cannot hold and re-run it in the log domain
         got, _ = _run(product, le, ls, None, None, "device", kind)
         # |LL| reaches several thousand here: one fp32 ulp of a log-domain quantity of that size is a few 1e-4 of its
         # exponential, so the element-wise bound is 3e-4 for this adversarial case (1e-4 everywhere else)
@@ -310,7 +310,7 @@ def test_tone_latent_infeasible(product, oracle_mod):
 
 # ---- split-role kernel (kind 4; kind 5 = 4 with the log-domain re-run forced) and wide lattices ----------------
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("B,T,U", [(3, 64, 64), (2, 9, 64), (5, 333, 128), (2, 801, 128), (3, 130, 128),
                                    (2, 700, 256), (1, 300, 256), (35, 200, 128)])
 def test_full_width_lattices_all_block_float_kernels(product, oracle_mod, kind, B, T, U):
@@ -338,7 +338,7 @@ def test_split_kernel_infeasible_and_masked(product, oracle_mod):
     ls[5, 40, :] = -np.inf                                 # no path at all → -inf
     le[0, 3, 2] = -np.inf
     want = oracle_mod.forward_backward(le, ls, t_len, u_len)
-    for kind in (2, 4, 5, 6, 7):
+    for kind in (2, 4, 5, 6, 7, 8, 9):
         got, used = _run(product, le, ls, t_len, u_len, "device", kind)
         assert used == kind
         _check(got, want, t_len, u_len)
