@@ -272,14 +272,16 @@ def run_reference(args):
 class Lattice:
     """Rotating input/output/scratch sets of one lattice workload on one GPU, and CUDA graphs over them."""
 
-    def __init__(self, P, dev, B, T, U, K, b_global0, set_stride, min_sets_bytes=3.2 * L2_BYTES, group=1, max_bytes=60e9):
+    def __init__(self, P, dev, B, T, U, K, b_global0, set_stride, min_sets_bytes=3.2 * L2_BYTES, group=1, max_bytes=60e9,
+                 logits=False):
         import torch
         self.P, self.dev, self.B, self.T, self.U, self.K = P, dev, B, T, U, K
         kk = K or 1
         self.cells = B * T * U
         self.ws_bytes = (P.tone_latent_forward_backward_workspace_bytes(B, T, U, K) if K
+                         else P.forward_backward_logits_workspace_bytes(B, T, U) if logits
                          else P.forward_backward_workspace_bytes(B, T, U))
-        self.set_bytes = self.cells * kk * 16 + self.ws_bytes
+        self.set_bytes = self.cells * kk * (8 if logits else 16) + self.ws_bytes
         n = max(1, int(np.ceil(min_sets_bytes / self.set_bytes)))
         n = ((n + group - 1) // group) * group            # whole graphs
         if self.set_bytes * n > max_bytes:
@@ -294,12 +296,17 @@ class Lattice:
                 inp = synthetic_tone_torch(b0, B, T, U, K, dev)
                 out = (torch.empty(B, device=dev), self.loss_all[s:s + 1], torch.empty(B, T, U, K, device=dev),
                        torch.empty(B, T, U, K, device=dev), torch.empty(B, U, K, device=dev))
+            elif logits:
+                le, ls = synthetic_torch(b0, B, T, U, dev)
+                inp = ((le - ls).contiguous(),)      # z = log sigmoid(z) - log sigmoid(-z)
+                del le, ls
+                out = (torch.empty(B, device=dev), self.loss_all[s:s + 1], torch.empty(B, T, U, device=dev))
             else:
                 inp = synthetic_torch(b0, B, T, U, dev)
                 out = (torch.empty(B, device=dev), self.loss_all[s:s + 1],
                        torch.empty(B, T, U, device=dev), torch.empty(B, T, U, device=dev))
             self.sets.append((inp, ws, out))
-        self.call = P.tone_latent_forward_backward if K else P.forward_backward
+        self.call = P.tone_latent_forward_backward if K else (P.forward_backward_logits if logits else P.forward_backward)
         self.graphs = []
 
     def run_set(self, i):
@@ -375,7 +382,7 @@ def launches_per_step(kind, K):
     return 2 if K else {6: 4, 8: 3}.get(kind, 1)
 
 
-def measure_lattice(P, dev, name, B, steps, warmup, world, rank, fb_kernel=-1, use_graph=True, exchange=False):
+def measure_lattice(P, dev, name, B, steps, warmup, world, rank, fb_kernel=-1, use_graph=True, exchange=False, logits=False):
     """Device-timed throughput of one lattice workload on this rank.  Returns a dict (per-rank numbers)."""
     import torch
     import torch.distributed as dist
@@ -385,7 +392,7 @@ def measure_lattice(P, dev, name, B, steps, warmup, world, rank, fb_kernel=-1, u
     g = graph_len(steps) if use_graph else 1
     P.set_fb_kernel(fb_kernel)
     # every rank and every set draws its own utterances from the global counter space
-    lat = Lattice(P, dev, B, T, U, K, b_global0=rank * B, set_stride=world * B, group=g)
+    lat = Lattice(P, dev, B, T, U, K, b_global0=rank * B, set_stride=world * B, group=g, logits=logits)
     for i in range(max(warmup, 3)):
         lat.run_set(i)
     torch.cuda.synchronize()
@@ -679,6 +686,25 @@ def run_b200(args):
             }
             del sm
             torch.cuda.empty_cache()
+        # raw-logit entry (one logit instead of two log-probs; 12 algorithmic bytes per cell) at the headline shape
+        lm = measure_lattice(P, dev, "cfg2", WORKLOADS["cfg2"][0], ssteps, 3, world, rank, exchange=world > 1, logits=True)
+        v = torch.tensor([lm["ms"], lm["kernel_ms"]], device=dev, dtype=torch.float64)
+        c = torch.tensor([float(lm["cells"])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c)
+        lach = 12 * lm["cells"] / (float(v[1].item()) * 1e-3) / 1e9
+        sec["cfg2_logits"] = {
+            "workload": "ssnt_tts_forward_backward_logits at the cfg2 shape (B=32 U=128 T=800 per GPU): log-sigmoids fused into "
+                        "the kernels, gradient chained through them",
+            "value": float(c.item()) * ssteps / (float(v[0].item()) * 1e-3), "unit": "cells/s",
+            "ms_per_step": float(v[0].item()) / ssteps, "steps": ssteps,
+            "roofline": {"bound": "hbm", "achieved": lach, "peak": peak, "unit": "GB/s", "frac": lach / peak,
+                         "kernel_ms": float(v[1].item()), "algorithmic_bytes_per_launch": 12 * lm["cells"],
+                         "note": "12 B/cell: read one logit, write one gradient (and the upstream log-sigmoid kernels disappear)"},
+            "loss_check": lm["loss_allreduced"]}
+        del lm
+        torch.cuda.empty_cache()
         if rank == 0:
             sec["cfg4_decoding"] = decoding_secondary(P, dev)
         line["secondary"] = sec

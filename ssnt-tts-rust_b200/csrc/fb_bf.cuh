@@ -459,7 +459,9 @@ __device__ void bf_lattice_cta(const BfParams& p, int b, unsigned rank, int T, i
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(smem_u32(raw_full + s), 1);
         fence_mbar_init();
-        if (rank == 0) p.status[b] = p.force_fallback ? (unsigned)kBfForced : 0u;
+        // (the status words are zeroed on the stream before the launch: a fault bit the partner CTA raises early
+        // cannot be wiped by a late reset here)
+        if (rank == 0 && p.force_fallback) atomicOr(p.status + b, (unsigned)kBfForced);
     }
     __syncthreads();
 

@@ -774,6 +774,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.scratch = (float*)ws;
         p.SU = round_up4(a.max_u) + 32;
         p.status = (unsigned*)((char*)ws + (size_t)a.batch_size * (a.max_t + 1) * p.SU * sizeof(float));
+        SSNT_CUDA(cudaMemsetAsync(p.status, 0, (size_t)a.batch_size * sizeof(unsigned), stream));  // the CTAs only OR into it
         p.fallbacks = device_fallback_counter();
         p.force_fallback = kind == 3 ? 1 : 0;  // kind 3: run the block-float kernel but force the log-domain re-run
         p.counter = counter;

@@ -577,9 +577,11 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         float e[CPL], s[CPL];
-        if constexpr (LG) {  // the logit rows stay in place: the beta sweep converts them again (it needs the unmasked pair)
+        if constexpr (LG) {  // the UNMASKED pair goes back to shared memory: the beta sweep chains the gradient through it
             float pu[CPL], qu[CPL];
             tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+            store_cells<CPL>(se + l * max_u, c0, max_u, pu);
+            store_cells<CPL>(ss + l * max_u, c0, max_u, qu);
         } else {
             tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
             store_cells<CPL>(se + l * max_u, c0, max_u, e);  // the raw rows are overwritten in place by the probabilities
@@ -601,8 +603,15 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     for (int l = L - 1; l >= 0; --l) {
         const int t = t0 + l;
         float e[CPL], s[CPL], pu[CPL], qu[CPL];
-        if constexpr (LG) {
-            tp_row_probs_logits<CPL>(se, l, t, T, U, max_u, c0, e, s, pu, qu);
+        if constexpr (LG) {  // sigmoid(+-z) as stored by the alpha sweep; the lattice's masks are re-applied here
+            load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, pu);
+            load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, qu);
+            const bool last = t == T - 1;
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                e[r] = t < T ? ((c0 + r < U) ? pu[r] : 0.0f) : 1.0f;
+                s[r] = (t < T && c0 + r < U - 1 && !last) ? qu[r] : 0.0f;
+            }
         } else {
             load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
             load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);

@@ -674,7 +674,10 @@ __global__ void __launch_bounds__(kTThreads, 1) tone_split_kernel(const ToneBfPa
         }
         if (rank == 0) {
             for (int i = tid; i < RW; i += kTThreads) a.grad_tone[(size_t)b * RW + i] = 0.0f;
-            if (tid == 0) a.log_likelihood[b] = -INFINITY;
+            if (tid == 0) {
+                a.log_likelihood[b] = -INFINITY;
+                p.status[b] = 0u;  // nothing to re-run: the follow-up log-domain kernel must not read an unwritten word
+            }
         }
     } else {
         for (int i = tid; i < (kTHeader - 128) / 4; i += kTThreads) reinterpret_cast<int*>(smem_raw + 128)[i] = 0;
