@@ -174,6 +174,10 @@ unsigned ssnt_tts_fb_fallback_count(void);
  * cycle counters (total, and cycles blocked on each hand-off barrier); NULL switches it off. */
 void ssnt_tts_debug_set_fb_stats(void *dev_buffer);
 const char *ssnt_tts_backend(void); /* "cuda-sm_100a" */
+/* Pre-fill of an int32 output in the memory space of `dst` (device: one small kernel on the current stream).  The
+ * reference's ops pre-fill on the host (ssnt_tts_beam_search_decode_op.cc:91, ssnt_tts_v2_beam_search_decode_op.cc:212,
+ * tone_latent_beam_search_decode_op.cc:168, upsample_source_indexes_op.cc:75); DEVICE_GPU registrations call this. */
+void ssnt_tts_fill_i32(int *dst, size_t n, int value);
 /* The host-to-host copy the host-pointer lattice calls stage pageable buffers with (spread over the library's copy
  * threads; SSNT_COPY_THREADS sets their number, the calling thread included).  Returns the thread count.  Test aid. */
 int ssnt_tts_debug_host_copy(void *dst, const void *src, size_t bytes);

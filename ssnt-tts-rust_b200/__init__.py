@@ -51,6 +51,7 @@ C_SYMBOLS = (
     "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
     "ssnt_tts_debug_host_copy",
+    "ssnt_tts_fill_i32",
     "ssnt_tts_v2_decode_loop",
     "ssnt_tts_forward_backward_logits_workspace_bytes",
     "ssnt_tts_forward_backward_logits",

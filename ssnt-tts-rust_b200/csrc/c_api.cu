@@ -24,6 +24,7 @@ void extract_best_beam_branch(int, const int*, const int*, int, int, int*, int*,
 void order_beam_branch(const int*, const int*, int, int, int, int*, cudaStream_t);
 void upsample_source_indexes(const int*, const int*, int, int, int, int, int*, cudaStream_t);
 void levenshtein_edit_distance(const int*, const int*, const int*, const int*, int, int, int*, cudaStream_t);
+void device_fill_i32(int*, size_t, int, cudaStream_t);
 void v2_decode_loop(const float*, const int*, const int*, const int*, const float*, const bool*, const int*, const int*,
                     const int*, int, int, int, int, int, bool, bool, int, int*, int*, float*, int*, int*, bool*, int*, int*,
                     int*, int*, cudaStream_t);
@@ -582,6 +583,14 @@ unsigned ssnt_tts_fb_fallback_count(void) {
     return read_fallback_counter();
 }
 const char* ssnt_tts_backend(void) { return "cuda-sm_100a"; }
+void ssnt_tts_fill_i32(int* dst, size_t n, int value) {
+    NOT_NULL(dst);
+    if (is_device_pointer(dst)) {
+        device_fill_i32(dst, n, value, current_stream());
+    } else {
+        for (size_t i = 0; i < n; ++i) dst[i] = value;
+    }
+}
 int ssnt_tts_debug_host_copy(void* dst, const void* src, size_t bytes) {
     NOT_NULL(dst); NOT_NULL(src);
     HostCopier c;

@@ -206,4 +206,18 @@ void upsample_source_indexes(const int* duration, const int* output_length, int 
     SSNT_CUDA(cudaGetLastError());
 }
 
+// Device-side pre-fill for the DEVICE_GPU op wrappers (the reference's ops pre-fill their outputs on the host:
+// ssnt_tts_beam_search_decode_op.cc:91, ssnt_tts_v2_beam_search_decode_op.cc:212, upsample_source_indexes_op.cc:75).
+namespace {
+__global__ void fill_i32_kernel(int* dst, size_t n, int value) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = value;
+}
+}  // namespace
+void device_fill_i32(int* dst, size_t n, int value, cudaStream_t stream) {
+    if (n == 0) return;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    fill_i32_kernel<<<blocks, 256, 0, stream>>>(dst, n, value);
+    SSNT_CUDA(cudaGetLastError());
+}
+
 }  // namespace ssnt
