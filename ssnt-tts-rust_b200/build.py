@@ -20,7 +20,10 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-fmad=true",
 ] + (["-DSSNT_BF_DEBUG_VARIANTS"] if os.environ.get("SSNT_BF_DEBUG_VARIANTS") else []) \
-  + (["-DSSNT_TP_TRACE"] if os.environ.get("SSNT_TP_TRACE") else [])
+  + (["-DSSNT_TP_TRACE"] if os.environ.get("SSNT_TP_TRACE") else []) \
+  + (["-DSSNT_TP_L=" + os.environ["SSNT_TP_L"]] if os.environ.get("SSNT_TP_L") else []) \
+  + (["-DSSNT_WS_BWD_STAGES=" + os.environ["SSNT_WS_BWD_STAGES"]] if os.environ.get("SSNT_WS_BWD_STAGES") else []) \
+  + (["-DSSNT_WS_FWD_STAGES=" + os.environ["SSNT_WS_FWD_STAGES"]] if os.environ.get("SSNT_WS_FWD_STAGES") else [])
 
 
 def _nvcc() -> str:

@@ -442,8 +442,8 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
 template <int CPL, int L>
 void launch_ws(const WsParams& p, cudaStream_t stream) {
     const FbArgs& a = p.a;
-    const size_t fwd_smem = 128 + (size_t)kWsFwdStages * 2 * p.R * a.max_u * sizeof(float);
-    const size_t bwd_smem = 128 + (size_t)2 * 2 * L * a.max_u * sizeof(float);
+    const size_t fwd_smem = 128 + (size_t)p.NS * 2 * p.R * a.max_u * sizeof(float);
+    const size_t bwd_smem = 128 + (size_t)kWsBwdStages * 2 * L * a.max_u * sizeof(float);
     static bool configured_[64] = {};  // per device
     bool& configured = configured_[device_ordinal()];
     if (!configured) {
@@ -640,10 +640,10 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     if (kind < 0) kind = bf_ok ? 6 : (warp_ok ? 1 : 0);
     // Large batches: the warp-serial kernels (kind 8) move 25 bytes per cell instead of ~37 and win once every SM holds
     // enough utterances to hide one warp's row latency.  Measured on B200 (G cells/s, kind 6 vs 8), T=2000 U=256:
-    // B=512 135/135, 1024 137/166, 2048 138/186, 4096 140/213; T=800 U=128: B=1024 157/123, 2048 161/170, 4096 163/190.
+    // B=512 135/137, 1024 137/212, 4096 140/232; T=800 U=128: B=1024 157/191, 4096 163/224.
     if (tls_force_kind < 0 && kind == 6 && !a.logits) {
         const size_t per_sm = (size_t)a.batch_size / (size_t)sm_count();
-        if ((a.max_u > 128 && per_sm >= 5) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 12)) kind = 8;
+        if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6)) kind = 8;
     }
     if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
         if (kind != 1 && kind != 6 && kind != 7) kind = bf_ok ? 6 : 1;
@@ -710,6 +710,9 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.C = wl.C;
         p.UP = wl.UP;
         p.R = wl.R;
+        // forward ring depth: 3 stages once an SM holds twenty utterances (B=4096 U=256: 232 vs 216 G cells/s), else 2
+        // so that more warps are resident (B=1024: 212 vs 201)
+        p.NS = (size_t)a.batch_size >= (size_t)20 * sm_count() ? 3 : 2;
         p.force_fallback = kind == 9 ? 1 : 0;  // kind 9: run the kernels but force the log-domain re-run
         if (wl.CPL == 2) launch_ws<2, 16>(p, stream);
         else if (wl.CPL == 4) launch_ws<4, 16>(p, stream);

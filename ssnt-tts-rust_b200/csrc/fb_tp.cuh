@@ -29,7 +29,10 @@
 namespace ssnt {
 namespace lattice {
 
-constexpr int kTpL = 16;               // frames per chunk
+#ifndef SSNT_TP_L
+#define SSNT_TP_L 16
+#endif
+constexpr int kTpL = SSNT_TP_L;        // frames per chunk
 constexpr float kTpRowTol = 2e-5f;     // |sum_u occupancy(t,u) - 1| beyond this flags the utterance
 constexpr float kTpZTol = 3e-5f;       // |log2 Z_forward - log2 Z_backward| beyond this flags it
 

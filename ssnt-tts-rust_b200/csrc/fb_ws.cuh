@@ -26,7 +26,12 @@ namespace lattice {
 
 constexpr int kWsGuard = 32;
 constexpr int kWsStageBytes = 8192;   // forward ring: rows per stage = kWsStageBytes / (8 * max_u)
-constexpr int kWsFwdStages = 3;
+constexpr int kWsFwdStagesMax = 3;     // forward ring stages: 3 when an SM holds many utterances, else 2 (WsParams::NS)
+#ifndef SSNT_WS_BWD_STAGES
+#define SSNT_WS_BWD_STAGES 1
+#endif
+constexpr int kWsBwdStages = SSNT_WS_BWD_STAGES;  // chunks in shared memory per warp in the backward kernel: one, so that
+                                                  // twice as many warps fit an SM (B=4096 U=256: 232 vs 213 G cells/s; B=1024: 201 vs 166)
 
 struct WsParams {
     FbArgs a;
@@ -36,6 +41,7 @@ struct WsParams {
     int C;             // checkpoints per utterance = ceil(max_t / L)
     int UP;            // padded token count = 32 * CPL
     int R;             // rows per forward ring stage
+    int NS;            // forward ring stages (<= kWsFwdStagesMax)
     int force_fallback;
 };
 
@@ -72,7 +78,7 @@ __device__ __forceinline__ void ws_renorm(float (&v)[CPL], int& F, float& kin, i
 template <int CPL, int L>
 __global__ void __launch_bounds__(32) ws_forward_kernel(const WsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int NS = kWsFwdStages;
+    const int NS = p.NS;
     constexpr int RN = CPL < 4 ? CPL : 4;  // rows between renormalisations: mass must not cross a whole lane in between
     const FbArgs& a = p.a;
     const int lane = threadIdx.x, b = blockIdx.x;
@@ -171,7 +177,8 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
     tp_pdl_trigger();  // the log-domain re-run kernel may be launched; it waits for this grid before reading status
     int T, U;
     const bool valid = tp_lengths(a, b, T, U);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [2]
+    constexpr int NSB = kWsBwdStages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // [NSB]
     float* ring = reinterpret_cast<float*>(smem_raw + 128);
     const int stage_floats = 2 * L * max_u;
     const int Cb = valid ? (T + L - 1) / L : 0;
@@ -181,11 +188,9 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
                        ring + (size_t)slot * stage_floats + L * max_u, smem_u32(bars + slot));
     };
     if (valid && lane == 0) {  // the raw rows do not depend on the forward kernel: start their copies now
-        mbar_init(smem_u32(bars), 1);
-        mbar_init(smem_u32(bars + 1), 1);
+        for (int i = 0; i < NSB; ++i) mbar_init(smem_u32(bars + i), 1);
         fence_mbar_init();
-        issue(Cb - 1, 0);
-        if (Cb >= 2) issue(Cb - 2, 1);
+        for (int i = 0; i < NSB && Cb - 1 - i >= 0; ++i) issue(Cb - 1 - i, i);
     }
     __syncwarp();
     tp_pdl_wait();  // the forward kernel has completed: checkpoints and likelihoods are visible
@@ -201,8 +206,7 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
     if (!(zf_lg > -1e30f) || p.force_fallback) {
         // no mass reached the end (a true -inf or an underflow): the log-domain kernel decides
         if (lane == 0) p.status[b] = p.force_fallback ? (unsigned)kTpForced : (unsigned)kTpBadZ;
-        mbar_wait_warp(smem_u32(bars), 0u);  // do not leave with bulk copies in flight
-        if (Cb >= 2) mbar_wait_warp(smem_u32(bars + 1), 0u);
+        for (int i = 0; i < NSB && Cb - 1 - i >= 0; ++i) mbar_wait_warp(smem_u32(bars + i), 0u);  // no bulk copy left in flight
         return;
     }
     if (lane == 0) a.log_likelihood[b] = (float)(((double)zf_lg + (double)zf_ex) * kLn2);
@@ -216,14 +220,14 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
     const float* ck = p.A + (size_t)b * (p.C + 1) * (UP + 32);
     float worst = 0.0f;
     for (int c = Cb - 1; c >= 0; --c) {
-        const int k = Cb - 1 - c, slot = k & 1;
+        const int k = Cb - 1 - c, slot = k % NSB;
         const int t0 = c * L;
         // the chunk's checkpoint (issued before the wait for the rows)
         float av[CPL];
         const float* arow = ck + (size_t)c * (UP + 32);
         tp_load<CPL>(arow + c0, av);
         int ea = reinterpret_cast<const int*>(arow + UP)[lane];
-        mbar_wait_warp(smem_u32(bars + slot), (unsigned)(k >> 1) & 1u);
+        mbar_wait_warp(smem_u32(bars + slot), (unsigned)(k / NSB) & 1u);
         float* se = ring + (size_t)slot * stage_floats;
         float* ss = se + L * max_u;
         // per-lane renormalisation (exact), then the frames held fixed over the chunk, one per lane:
@@ -327,9 +331,9 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
         eb = fb;  // beta(t0) now sits in frame fb
         // the slot is free: fetch the chunk after next (generic-proxy writes above must not overtake the bulk copy)
         __syncwarp();
-        if (lane == 0 && c - 2 >= 0) {
+        if (lane == 0 && c - NSB >= 0) {
             fence_proxy_async();
-            issue(c - 2, slot);
+            issue(c - NSB, slot);
         }
     }
     // backward likelihood beta_0(0) against the forward one
