@@ -164,7 +164,8 @@ unsigned ssnt_tts_last_error(void);
  * over the chunk boundaries, chunk interiors filled independently; the auto choice whenever
  * max_u % 4 == 0 and max_u <= 256), 7 = 6 with forced log re-run, 8 warp-serial block-float (one warp
  * per utterance, alpha checkpoints forward, chunked beta + gradients backward: 25 bytes per cell of
- * memory traffic; the auto choice for large batches), 9 = 8 with forced log re-run. */
+ * memory traffic; the auto choice for large batches), 9 = 8 with forced log re-run, 10 = 6 with 8-frame
+ * chunks (max_u > 128 only; what 6 picks by itself for wide lattices at medium batch sizes). */
 void ssnt_tts_set_fb_kernel(int kind);
 int ssnt_tts_get_fb_kernel_used(void);
 /* Cumulative number of utterances the block-float kernel had to re-run in the log domain

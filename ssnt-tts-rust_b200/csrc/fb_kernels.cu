@@ -380,9 +380,8 @@ void launch_split(const SplitParams& p, size_t smem, cudaStream_t stream) {
 inline int round_up4(int x) { return (x + 3) & ~3; }
 
 // Time-parallel path (kind 6): chunk operators, boundary vectors, chunk interiors; one warp per CTA throughout.
-template <int CPL>
+template <int CPL, int L = kTpL>
 void launch_tp(const TpParams& p, cudaStream_t stream) {
-    constexpr int L = kTpL;
     const FbArgs& a = p.a;
     const size_t chunk_smem = 128 + (size_t)2 * L * a.max_u * sizeof(float);
     constexpr int NT = 32 * CPL;
@@ -475,13 +474,14 @@ struct TpLayout {
     int CPL, UP, C, SU;
     size_t region0, vec, total;
 };
-static bool tp_layout(int B, int max_t, int max_u, TpLayout& l) {
+constexpr int kTpLShort = 8;  // chunk length for wide lattices at medium batch sizes (half the operator work)
+static bool tp_layout(int B, int max_t, int max_u, TpLayout& l, int L = kTpL) {
     if (max_u % 4 != 0 || max_u > 256 || max_u <= 0 || max_t <= 0 || B <= 0) return false;
     l.CPL = max_u <= 64 ? 2 : (max_u <= 128 ? 4 : 8);
     l.UP = 32 * l.CPL;
-    l.C = (max_t + kTpL - 1) / kTpL;
+    l.C = (max_t + L - 1) / L;
     l.SU = max_u + 32;
-    const size_t q = (size_t)B * l.C * (kTpL + 1) * l.UP * sizeof(float);
+    const size_t q = (size_t)B * l.C * (L + 1) * l.UP * sizeof(float);
     const size_t scr = (size_t)B * (max_t + 1) * l.SU * sizeof(float);
     l.region0 = ((q > scr ? q : scr) + 255) & ~(size_t)255;
     l.vec = (((size_t)B * (l.C + 1) * (l.UP + 32) * sizeof(float)) + 255) & ~(size_t)255;
@@ -534,6 +534,7 @@ size_t fb_workspace_bytes(int B, int max_t, int max_u) {
     n = n > split_bytes ? n : split_bytes;
     TpLayout tl;
     if (tp_layout(B, max_t, max_u, tl)) n = n > tl.total ? n : tl.total;
+    if (tp_layout(B, max_t, max_u, tl, kTpLShort)) n = n > tl.total ? n : tl.total;
     WsLayout wl;
     if (ws_layout(B, max_t, max_u, wl)) n = n > wl.total ? n : wl.total;
     return (n + 255) & ~(size_t)255;
@@ -646,11 +647,17 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6)) kind = 8;
     }
     if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
-        if (kind != 1 && kind != 6 && kind != 7) kind = bf_ok ? 6 : 1;
+        if (kind != 1 && kind != 6 && kind != 7 && kind != 10) kind = bf_ok ? 6 : 1;
     }
-    if (kind == 6 || kind == 7) {
+    if (kind == 6 || kind == 7 || kind == 10) {
+        // Chunk length: 16 frames, except 8 for wide lattices (max_u > 128) once the sweeps no longer have an SM each —
+        // the operators then cost half as much to build and the 2x longer sweep hides behind other utterances
+        // (B=512 U=256 T=2000: 1.57 vs 1.95 ms).  Kind 10 forces the short chunks (max_u > 128 only).
+        const bool short_chunks = a.max_u > 128 && (kind == 10 || (kind == 6 && tls_force_kind < 0 && (size_t)a.batch_size * 2 > (size_t)sm_count()));
+        SSNT_ASSERT(kind != 10 || a.max_u > 128, "forward_backward: kind 10 (8-frame chunks) needs max_u > 128");
+        const int L = short_chunks ? kTpLShort : kTpL;
         TpLayout tl;
-        SSNT_ASSERT(bf_ok && tp_layout(a.batch_size, a.max_t, a.max_u, tl), "forward_backward: time-parallel kernels forced on an unsupported shape");
+        SSNT_ASSERT(bf_ok && tp_layout(a.batch_size, a.max_t, a.max_u, tl, L), "forward_backward: time-parallel kernels forced on an unsupported shape");
         tls_last_kind = kind;
         TpParams p;
         p.a = a;
@@ -662,7 +669,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.status = (unsigned*)(base + tl.region0 + 2 * tl.vec + (((size_t)a.batch_size * 4 * sizeof(float) + 255) & ~(size_t)255));
         p.C = tl.C;
         p.UP = tl.UP;
-        const size_t stage = (size_t)(kTpL + 1) * tl.UP * sizeof(float);
+        const size_t stage = (size_t)(L + 1) * tl.UP * sizeof(float);
         int NS = (int)((size_t)(200 * 1024) / stage);
         p.NS = NS > 16 ? 16 : NS;
         p.debug = 0;
@@ -673,6 +680,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
         if (tl.CPL == 2) launch_tp<2>(p, stream);
         else if (tl.CPL == 4) launch_tp<4>(p, stream);
+        else if (short_chunks) launch_tp<8, kTpLShort>(p, stream);
         else launch_tp<8>(p, stream);
         // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
 #ifdef SSNT_BF_DEBUG_VARIANTS
@@ -735,7 +743,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         else launch_warp<8>(lp, smem, stream, true);
         return;
     }
-    SSNT_ASSERT(kind <= 7, "forward_backward: unknown kernel kind (0 .. 9)");
+    SSNT_ASSERT(kind <= 7, "forward_backward: unknown kernel kind (0 .. 10)");
     if (kind >= 4) SSNT_ASSERT(split_ok && a.batch_size <= 64, "forward_backward: split kernel forced on an unsupported shape");
     if (kind == 1) SSNT_ASSERT(warp_ok, "forward_backward: warp kernel forced on an unsupported shape");
     if (kind >= 2) SSNT_ASSERT(bf_ok, "forward_backward: block-float kernel forced on an unsupported shape");

@@ -540,7 +540,8 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     // Frames held fixed over the chunk, one per lane: F_l = max(ex_l, F_{l-1} - dec) for alpha (mass arrives from
     // the left), F_l = max(ex_l, F_{l+1} - dec) for beta (from the right): a lane the front has not reached takes
     // its neighbour's frame lowered by dec, so that what enters it within L rows neither overflows nor flushes.
-    constexpr int kDec = 96 / ((L + CPL - 1) / CPL);
+    constexpr int kDec0 = 96 / ((L + CPL - 1) / CPL);
+    constexpr int kDec = kDec0 < 48 ? kDec0 : 48;
     int fa = ea + kDec * lane;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

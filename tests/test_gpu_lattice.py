@@ -548,3 +548,21 @@ def test_logit_entry_host_pointers_and_extreme_logits(product, oracle_mod):
     _check_logits(got, z, want, t_len)
     got = product.forward_backward_logits(_dev(z), _dev(t_len), _dev(u_len))
     _check_logits(got, z, want, t_len)
+
+
+# ---- 8-frame chunks of the time-parallel kernels (kind 10; the auto choice for wide lattices at medium batch sizes) ---
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,T,U", [(2, 700, 256), (1, 300, 256), (3, 2000, 256), (5, 333, 200), (2, 97, 132), (80, 120, 160)])
+def test_short_chunk_time_parallel_kernels(product, oracle_mod, B, T, U):
+    le, ls = make_inputs(B, T, U, seed=T * 3 + U + B)
+    t_len, u_len = ragged_lengths(B, T, U, seed=T + B)
+    t_len[0], u_len[0] = T, min(U, T)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, used = _run(product, le, ls, t_len, u_len, "device", 10)
+    assert used == 10
+    _check(got, want, t_len, u_len)
+    if B == 80:   # more sweeps than SMs: the auto choice takes the short chunks too (kind 6 reported)
+        fb0 = product.fb_fallback_count()
+        got, used = _run(product, le, ls, t_len, u_len, "device")
+        assert used == 6 and product.fb_fallback_count() == fb0
+        _check(got, want, t_len, u_len)
