@@ -196,68 +196,129 @@ __device__ bool beam_step_warp(const BeamParams& p, const Table& tb, const BeamR
     }
     __syncwarp();
 
-    // ---- 2. compact valid slots, keeping (w, class) order -----------------------------------
-    int n = 0;
-    for (int s0 = 0; s0 < N; s0 += 32) {
-        const int s = s0 + lane;
-        const bool v = s < N && tb.valid[s];
-        const unsigned bal = __ballot_sync(kFull, v);
-        if (v) {
-            const int k = n + __popc(bal & ((1u << lane) - 1u));
-            tb.tmp[k] = s;
-            // Sort keys form a total order: the reference's comparator (partial_cmp().unwrap_or(Equal), src/lib.rs:161)
-            // leaves the position of NaN log-probs to its sort algorithm; here NaN ranks below everything, after -inf
-            // entries of the same run, so the ranks below are always a permutation.
-            const float k0 = tb.lp[s];
-            tb.key[k] = (k0 != k0) ? -INFINITY : k0;
-        }
-        n += __popc(bal);
-    }
-    __syncwarp();
-    if (n == 0) {  // src/v2.rs:292 assert_ne! / `i % 0` in src/tone_latent.rs:199
-        if (lane == 0) atomicOr(p.err, V == kV2 ? kErrV2EmptyBeam : kErrToneEmptyBeam);
-        return false;
-    }
-    // ---- 3. stable descending sort: rank = #{j : lp_j > lp_i or (lp_j == lp_i and j before i)} ---
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const float mine = i < n ? tb.key[i] : 0.0f;
-        int rank = 0;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-            const float other = tb.key[j];  // same address across the warp → broadcast
-            rank += (other > mine || (other == mine && j < i)) ? 1 : 0;
-        }
-        if (i < n) tb.order[rank] = tb.tmp[i];
-    }
-    __syncwarp();
-    // ---- 4. drop consecutive duplicates (first of a run survives) ------------------------------
-    int kept = 0;
-    for (int r0 = 0; r0 < n; r0 += 32) {
-        const int q = r0 + lane;
-        bool keep = false;
-        int slot = 0;
-        if (q < n) {
-            slot = tb.order[q];
-            keep = q == 0 || !same_bucket(tb, slot, tb.order[q - 1]);
-        }
-        const unsigned bal = __ballot_sync(kFull, keep);
-        if (keep) tb.tmp[kept + __popc(bal & ((1u << lane) - 1u))] = slot;
-        kept += __popc(bal);
-    }
-    __syncwarp();
-    // ---- 5. v2: first survivor on the diagonal ---------------------------------------------------
-    int diag = -1;
-    if (V == kV2 && !p.test_mode) {
-        for (int r0 = 0; r0 < kept && diag < 0; r0 += 32) {
-            const int q = r0 + lane;
-            bool on = false;
-            if (q < kept) {
-                const int s = tb.tmp[q];
-                on = v2_on_diagonal((int)in_len, (int)out_len, tb.nt[s], tb.tot[s]);
+    int kept = 0, diag = -1;
+    if (N <= 64) {
+        // Few candidates (e.g. the tone-latent step, 8 beams x 4 tones): a full stable sort by rank counting is cheaper
+        // than the extraction rounds below.
+        // ---- 2. compact valid slots, keeping (w, class) order -----------------------------------
+        int n = 0;
+        for (int s0 = 0; s0 < N; s0 += 32) {
+            const int s = s0 + lane;
+            const bool v = s < N && tb.valid[s];
+            const unsigned bal = __ballot_sync(kFull, v);
+            if (v) {
+                const int k = n + __popc(bal & ((1u << lane) - 1u));
+                tb.tmp[k] = s;
+                // Sort keys form a total order: the reference's comparator (partial_cmp().unwrap_or(Equal), src/lib.rs:161)
+                // leaves the position of NaN log-probs to its sort algorithm; here NaN ranks below everything, after -inf
+                // entries of the same run, so the ranks below are always a permutation.
+                const float k0 = tb.lp[s];
+                tb.key[k] = (k0 != k0) ? -INFINITY : k0;
             }
-            const unsigned bal = __ballot_sync(kFull, on);
-            if (bal) diag = tb.tmp[r0 + __ffs(bal) - 1];
+            n += __popc(bal);
+        }
+        __syncwarp();
+        if (n == 0) {  // src/v2.rs:292 assert_ne! / `i % 0` in src/tone_latent.rs:199
+            if (lane == 0) atomicOr(p.err, V == kV2 ? kErrV2EmptyBeam : kErrToneEmptyBeam);
+            return false;
+        }
+        // ---- 3. stable descending sort: rank = #{j : lp_j > lp_i or (lp_j == lp_i and j before i)} ---
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const float mine = i < n ? tb.key[i] : 0.0f;
+            int rank = 0;
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) {
+                const float other = tb.key[j];  // same address across the warp → broadcast
+                rank += (other > mine || (other == mine && j < i)) ? 1 : 0;
+            }
+            if (i < n) tb.order[rank] = tb.tmp[i];
+        }
+        __syncwarp();
+        // ---- 4. drop consecutive duplicates (first of a run survives) ------------------------------
+        for (int r0 = 0; r0 < n; r0 += 32) {
+            const int q = r0 + lane;
+            bool keep = false;
+            int slot = 0;
+            if (q < n) {
+                slot = tb.order[q];
+                keep = q == 0 || !same_bucket(tb, slot, tb.order[q - 1]);
+            }
+            const unsigned bal = __ballot_sync(kFull, keep);
+            if (keep) tb.tmp[kept + __popc(bal & ((1u << lane) - 1u))] = slot;
+            kept += __popc(bal);
+        }
+        __syncwarp();
+        // ---- 5. v2: first survivor on the diagonal ---------------------------------------------------
+        if (V == kV2 && !p.test_mode) {
+            for (int r0 = 0; r0 < kept && diag < 0; r0 += 32) {
+                const int q = r0 + lane;
+                bool on = false;
+                if (q < kept) {
+                    const int s = tb.tmp[q];
+                    on = v2_on_diagonal((int)in_len, (int)out_len, tb.nt[s], tb.tot[s]);
+                }
+                const unsigned bal = __ballot_sync(kFull, on);
+                if (bal) diag = tb.tmp[r0 + __ffs(bal) - 1];
+            }
+        }
+    } else {
+        // ---- 2-5. the first W survivors of "stable sort by log-prob descending, then drop an element equal to the one
+        // before it" WITHOUT sorting everything: candidates are extracted one by one in sorted order — a warp arg-max over
+        // (key descending, slot ascending), which is exactly the stable order since slots are in (w, class) order — and
+        // each is kept unless it equals the last kept one (an equivalence, so "last kept" and "immediately preceding"
+        // agree).  W + (duplicates met) rounds of two warp reductions instead of N^2/32 comparisons per lane.
+        // Keys form a total order: -0.0 counts as +0.0 (partial_cmp says Equal); NaN, whose position the reference's
+        // comparator (partial_cmp().unwrap_or(Equal), src/lib.rs:161) leaves to its sort algorithm, ranks below everything.
+        auto okey = [&](int slot) -> unsigned {
+            float k0 = tb.lp[slot] + 0.0f;
+            k0 = (k0 != k0) ? -INFINITY : k0;
+            const unsigned bits = __float_as_uint(k0);
+            return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);   // order-preserving image of the float
+        };
+        // this lane's best live candidate among its slots lane, lane+32, ...  (0 / -1 if none)
+        auto lane_best = [&](unsigned& bk, int& bs) {
+            bk = 0u; bs = -1;
+            for (int s2 = lane; s2 < N; s2 += 32) {
+                if (!tb.valid[s2]) continue;
+                const unsigned k2 = okey(s2);
+                if (bs < 0 || k2 > bk) { bk = k2; bs = s2; }   // ascending scan: the first of equal keys stays
+            }
+        };
+        // v2: the first survivor on the diagonal = the best on-diagonal candidate (it cannot be a duplicate of the element
+        // before it, which would be on the diagonal too and earlier)
+        if (V == kV2 && !p.test_mode) {
+            unsigned bk = 0u; int bs = -1;
+            for (int s2 = lane; s2 < N; s2 += 32) {
+                if (!tb.valid[s2] || !v2_on_diagonal((int)in_len, (int)out_len, tb.nt[s2], tb.tot[s2])) continue;
+                const unsigned k2 = okey(s2);
+                if (bs < 0 || k2 > bk) { bk = k2; bs = s2; }
+            }
+            const unsigned top = __reduce_max_sync(kFull, bs >= 0 ? bk : 0u);
+            const int first = (int)__reduce_min_sync(kFull, (bs >= 0 && bk == top) ? (unsigned)bs : 0xffffffffu);
+            diag = __any_sync(kFull, bs >= 0) ? first : -1;
+        }
+        unsigned bk; int bs;
+        lane_best(bk, bs);
+        int last = -1;
+        for (;;) {
+            if (!__any_sync(kFull, bs >= 0)) break;   // every candidate extracted
+            const unsigned top = __reduce_max_sync(kFull, bs >= 0 ? bk : 0u);
+            const int slot = (int)__reduce_min_sync(kFull, (bs >= 0 && bk == top) ? (unsigned)bs : 0xffffffffu);
+            if (last < 0 || !same_bucket(tb, slot, last)) {
+                if (lane == 0) tb.tmp[kept] = slot;
+                last = slot;
+                if (++kept == W) break;
+            }
+            if (slot % 32 == lane) {   // the owner retires it and looks for its next best
+                tb.valid[slot] = 0;
+                lane_best(bk, bs);
+            }
+        }
+        __syncwarp();
+        if (kept == 0) {  // src/v2.rs:292 assert_ne! / `i % 0` in src/tone_latent.rs:199
+            if (lane == 0) atomicOr(p.err, V == kV2 ? kErrV2EmptyBeam : kErrToneEmptyBeam);
+            return false;
         }
     }
     // ---- 6. pad cyclically, truncate, append the diagonal candidate last -------------------------
@@ -346,7 +407,8 @@ __global__ void __launch_bounds__(32) decode_loop_kernel(const LoopParams lp) {
     int* s_t = s_total + 2 * WP;
     int* s_u = s_t + 2 * WP;
     bool* s_fin = reinterpret_cast<bool*>(s_u + 2 * WP);
-    int* s_ph = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_fin) + 2 * WP);  // [S, W] if hist_in_smem
+    float* s_h = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_fin) + 2 * WP);   // [2][N] scores of this / the next step
+    int* s_ph = reinterpret_cast<int*>(s_h + 2 * (size_t)N);  // [S, W] if hist_in_smem
     int* s_bh = s_ph + (lp.hist_in_smem ? (size_t)S * W : 0);
     const size_t ob = (size_t)b * W;
     for (int w = lane; w < W; w += 32) {
@@ -356,6 +418,16 @@ __global__ void __launch_bounds__(32) decode_loop_kernel(const LoopParams lp) {
         s_u[w] = p.u ? p.u[ob + w] : 0;
         s_fin[w] = p.fin ? p.fin[ob + w] : false;
     }
+    // the step's scores travel global -> shared memory asynchronously, one step ahead of their use
+    const float* hb = p.h + (size_t)b * S * N;
+    auto fetch = [&](int s) {
+        float* dst = s_h + (size_t)(s & 1) * N;
+        const float* src = hb + (size_t)s * N;
+        for (int i = lane; i < N; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
     __syncwarp();
     const long long in_len = (long long)p.in_len[b];
     const long long out_len = V == kV2 ? (long long)p.out_len[b] : 0;
@@ -364,14 +436,20 @@ __global__ void __launch_bounds__(32) decode_loop_kernel(const LoopParams lp) {
     int cur = 0;
     for (int s = 0; s < S; ++s) {
         const int nxt = cur ^ 1;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (s + 1 < S) fetch(s + 1);
         BeamRow r;
-        r.h = p.h + ((size_t)b * S + s) * N;
+        r.h = s_h + (size_t)(s & 1) * N;
         r.hist = s_hist + cur * WP; r.fin = s_fin + cur * WP; r.total = s_total + cur * WP; r.t = s_t + cur * WP; r.u = s_u + cur * WP;
         r.prediction = lp.hist_in_smem ? s_ph + (size_t)s * W : gph + (size_t)s * W;
         r.parent = lp.hist_in_smem ? s_bh + (size_t)s * W : gbh + (size_t)s * W;
         r.log_probs = s_hist + nxt * WP; r.next_t = s_t + nxt * WP; r.next_u = s_u + nxt * WP;
         r.next_fin = s_fin + nxt * WP; r.next_total = s_total + nxt * WP;
-        if (!beam_step_warp<V>(p, tb, r, in_len, out_len, lane)) return;  // flag raised; the reference would have panicked here
+        if (!beam_step_warp<V>(p, tb, r, in_len, out_len, lane)) {  // flag raised; the reference would have panicked here
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            return;
+        }
         __syncwarp();
         if (lp.hist_in_smem)
             for (int w = lane; w < W; w += 32) {
@@ -446,7 +524,7 @@ void launch_loop(LoopParams lp, cudaStream_t stream) {
     const BeamParams& p = lp.bp;
     if (p.B <= 0 || p.W <= 0 || lp.S <= 0) return;
     const size_t WP = (size_t)((p.W + 3) & ~3);
-    const size_t base = table_bytes((size_t)p.W * p.C) + 2 * WP * (4 * 4 + 1) + 16;
+    const size_t base = table_bytes((size_t)p.W * p.C) + 2 * WP * (4 * 4 + 1) + 16 + (size_t)2 * p.W * p.C * sizeof(float);
     const size_t hist = (size_t)2 * lp.S * p.W * sizeof(int);
     lp.hist_in_smem = base + hist <= 200 * 1024 ? 1 : 0;
     const size_t smem = base + (lp.hist_in_smem ? hist : 0);
