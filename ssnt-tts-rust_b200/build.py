@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-fmad=true",
 ] + (["-DSSNT_BF_DEBUG_VARIANTS"] if os.environ.get("SSNT_BF_DEBUG_VARIANTS") else []) \
   + (["-DSSNT_TP_TRACE"] if os.environ.get("SSNT_TP_TRACE") else []) \
+  + (["-DSSNT_TP_TIMING"] if os.environ.get("SSNT_TP_TIMING") else []) \
   + (["-DSSNT_TP_L=" + os.environ["SSNT_TP_L"]] if os.environ.get("SSNT_TP_L") else []) \
   + (["-DSSNT_WS_BWD_STAGES=" + os.environ["SSNT_WS_BWD_STAGES"]] if os.environ.get("SSNT_WS_BWD_STAGES") else []) \
   + (["-DSSNT_WS_FWD_STAGES=" + os.environ["SSNT_WS_FWD_STAGES"]] if os.environ.get("SSNT_WS_FWD_STAGES") else [])

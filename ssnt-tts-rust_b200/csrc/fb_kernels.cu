@@ -380,15 +380,15 @@ void launch_split(const SplitParams& p, size_t smem, cudaStream_t stream) {
 inline int round_up4(int x) { return (x + 3) & ~3; }
 
 // Time-parallel path (kind 6): chunk operators, boundary vectors, chunk interiors; one warp per CTA throughout.
-template <int CPL, int L = kTpL>
+template <int CPL, int L = kTpL, int G = (32 * CPL <= 128 ? 32 : 16)>
 void launch_tp(const TpParams& p, cudaStream_t stream) {
     const FbArgs& a = p.a;
     const size_t chunk_smem = 128 + (size_t)2 * L * a.max_u * sizeof(float);
     constexpr int NT = 32 * CPL;
     constexpr int NS = NT <= 128 ? 16 : 8;   // 139 KB of operators in flight per (utterance, direction)
-    // Exponent granularity of the boundary vectors: a warp's 32 tokens for max_u <= 128; half a warp for wider
-    // lattices, whose long sweeps (T = 2000 at U = 256) lost ~1e-4 of the likelihood with 32-token groups.
-    constexpr int G = NT <= 128 ? 32 : 16;
+    // Exponent granularity of the boundary vectors (G): a warp's 32 tokens for short sweeps of narrow lattices, half a
+    // warp otherwise — long sweeps lose likelihood with 32-token groups (T = 2000 at U = 256: ~1e-4; T = 1000 at U = 128:
+    // 5 of 1184 random utterances missed the 3e-5 agreement of the two sweeps and were re-run), see the call sites.
     const size_t ring_smem = 512 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
     static size_t configured_[64] = {};  // per device
     size_t& configured = configured_[device_ordinal()];
@@ -678,8 +678,11 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.debug = k2dbg;
 #endif
         p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
-        if (tl.CPL == 2) launch_tp<2>(p, stream);
-        else if (tl.CPL == 4) launch_tp<4>(p, stream);
+        // 32-token exponent groups only while the sweeps are short (<= 50 steps: no re-run in 4800 random utterances at
+        // T = 800; the per-step cost is ~10 % lower than with 16-token groups)
+        const bool wide_groups = a.max_t <= 50 * kTpL;
+        if (tl.CPL == 2) { if (wide_groups) launch_tp<2>(p, stream); else launch_tp<2, kTpL, 16>(p, stream); }
+        else if (tl.CPL == 4) { if (wide_groups) launch_tp<4>(p, stream); else launch_tp<4, kTpL, 16>(p, stream); }
         else if (short_chunks) launch_tp<8, kTpLShort>(p, stream);
         else launch_tp<8>(p, stream);
         // the log-domain kernel re-runs what was flagged (status != 0) and reduces the loss
