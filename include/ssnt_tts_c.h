@@ -168,6 +168,13 @@ unsigned ssnt_tts_last_error(void);
  * chunks (max_u > 128 only; what 6 picks by itself for wide lattices at medium batch sizes). */
 void ssnt_tts_set_fb_kernel(int kind);
 int ssnt_tts_get_fb_kernel_used(void);
+/* Tone-latent lattice kernel selection for tests/benchmarks: -1 auto, 0 log domain only, 1 block-float split-role
+ * (cluster of four CTAs per utterance; K = 4, max_u in {32,64,128}; the auto choice for small batches), 2 block-float
+ * warp-serial (one warp per utterance, alpha checkpoints forward, chunked beta + gradients backward; K in {2,4,8},
+ * max_u in {32,64,128,256} with 4 <= max_u*K/32 <= 32; the auto choice from two utterances per SM and for every shape
+ * 1 does not take), 3 = 2 with every utterance re-run in the log domain. */
+void ssnt_tts_set_tone_kernel(int kind);
+int ssnt_tts_get_tone_kernel_used(void);
 /* Cumulative number of utterances the block-float kernel had to re-run in the log domain
  * because their dynamic range did not fit (waits for the current stream). */
 unsigned ssnt_tts_fb_fallback_count(void);

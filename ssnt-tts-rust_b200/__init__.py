@@ -47,6 +47,8 @@ C_SYMBOLS = (
     "ssnt_tts_last_error",
     "ssnt_tts_set_fb_kernel",
     "ssnt_tts_get_fb_kernel_used",
+    "ssnt_tts_set_tone_kernel",
+    "ssnt_tts_get_tone_kernel_used",
     "ssnt_tts_fb_fallback_count",
     "ssnt_tts_debug_set_fb_stats",
     "ssnt_tts_backend",
@@ -98,6 +100,7 @@ def lib() -> ctypes.CDLL:
         L.ssnt_tts_set_stream.argtypes = [c_void_p]
         L.ssnt_tts_last_error.restype = c_uint
         L.ssnt_tts_get_fb_kernel_used.restype = c_int
+        L.ssnt_tts_get_tone_kernel_used.restype = c_int
         L.ssnt_tts_fb_fallback_count.restype = c_uint
         L.ssnt_tts_backend.restype = ctypes.c_char_p
         _lib = L
@@ -169,6 +172,16 @@ def set_fb_kernel(kind: int) -> None:
 
 def fb_kernel_used() -> int:
     return int(lib().ssnt_tts_get_fb_kernel_used())
+
+
+def set_tone_kernel(kind: int) -> None:
+    """Tone-latent lattice kernel for tests/benchmarks: -1 auto, 0 log domain, 1 split-role block-float, 2 warp-serial
+    block-float, 3 = 2 with every utterance re-run in the log domain (include/ssnt_tts_c.h)."""
+    lib().ssnt_tts_set_tone_kernel(c_int(kind))
+
+
+def tone_kernel_used() -> int:
+    return int(lib().ssnt_tts_get_tone_kernel_used())
 
 
 def fb_fallback_count() -> int:

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssnt_tts_c.so")
-SOURCES = ["runtime.cu", "host_copy.cu", "fb_kernels.cu", "tone_fb_kernels.cu", "tone_bf.cu", "beam_kernels.cu", "trace_kernels.cu",
+SOURCES = ["runtime.cu", "host_copy.cu", "fb_kernels.cu", "tone_fb_kernels.cu", "tone_bf.cu", "tone_ws.cu", "beam_kernels.cu", "trace_kernels.cu",
            "edit_distance.cu", "c_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -578,6 +578,8 @@ unsigned ssnt_tts_last_error(void) {
 void ssnt_tts_set_fb_kernel(int kind) { fb_force_kernel_kind(kind); }
 void ssnt_tts_debug_set_fb_stats(void* dev_buffer) { fb_set_stats_buffer((long long*)dev_buffer); }
 int ssnt_tts_get_fb_kernel_used(void) { return fb_last_kernel_kind(); }
+void ssnt_tts_set_tone_kernel(int kind) { tone_force_kernel_kind(kind); }
+int ssnt_tts_get_tone_kernel_used(void) { return tone_last_kernel_kind(); }
 unsigned ssnt_tts_fb_fallback_count(void) {
     SSNT_CUDA(cudaStreamSynchronize(current_stream()));
     return read_fallback_counter();

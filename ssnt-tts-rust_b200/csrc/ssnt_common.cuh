@@ -161,6 +161,16 @@ size_t tone_fb_workspace_bytes(int batch_size, int max_t, int max_u, int tone_cl
 bool tone_bf_supported(const ToneFbArgs& a);
 size_t tone_bf_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
 unsigned* launch_tone_bf(const ToneFbArgs& a, void* workspace, unsigned* counter, cudaStream_t stream);
+// warp-serial block-float tone kernels (tone_ws.cu): the large-batch path and every K in {2,4,8} / max_u in {32..256}
+bool tone_ws_supported(const ToneFbArgs& a);
+size_t tone_ws_workspace_bytes(int batch_size, int max_t, int max_u, int tone_class_size);
+unsigned* launch_tone_ws(const ToneFbArgs& a, void* workspace, int force_fallback, cudaStream_t stream);
+// tone kernel selection for tests/benchmarks: -1 auto, 0 log-domain only, 1 split-role block-float, 2 warp-serial
+// block-float, 3 = 2 with every utterance re-run in the log domain
+void tone_force_kernel_kind(int kind);
+int tone_forced_kernel_kind();
+int tone_last_kernel_kind();
+void tone_note_kernel_kind(int kind);
 void launch_tone_forward_backward(const ToneFbArgs& a, cudaStream_t stream);
 
 }  // namespace ssnt

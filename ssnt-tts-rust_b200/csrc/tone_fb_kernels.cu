@@ -346,7 +346,8 @@ size_t tone_fb_workspace_bytes(int B, int max_t, int max_u, int K) {
     if (B <= 0 || max_t <= 0 || max_u <= 0 || K <= 0) return 256;
     size_t n = ((size_t)B * max_t * max_u * K + (size_t)B * max_t) * sizeof(float);
     n = (n + 255) & ~(size_t)255;
-    return n + tone_bf_workspace_bytes(B, max_t, max_u, K);
+    const size_t bf = (tone_bf_workspace_bytes(B, max_t, max_u, K) + 255) & ~(size_t)255;
+    return n + bf + tone_ws_workspace_bytes(B, max_t, max_u, K);
 }
 
 void launch_tone_forward_backward(const ToneFbArgs& a_in, cudaStream_t stream) {
@@ -366,11 +367,22 @@ void launch_tone_forward_backward(const ToneFbArgs& a_in, cudaStream_t stream) {
     }
     const int K = a.tone_class_size;
     const size_t log_bytes = (((size_t)a.batch_size * a.max_t * a.max_u * K + (size_t)a.batch_size * a.max_t) * sizeof(float) + 255) & ~(size_t)255;
-    // Block-float split-role kernel first (tone_bf.cu); the log-domain kernel then redoes only what it flagged.
+    // A block-float path first; the log-domain kernel then redoes only what it flagged.  Warp-serial kernels (tone_ws.cu)
+    // once there are at least two utterances per SM, and for every shape the split-role kernel (tone_bf.cu: K = 4,
+    // max_u in {32,64,128}, a cluster of four CTAs per utterance) does not take.
     const unsigned* only = nullptr;
-    bool use_bf = tone_bf_supported(a) && (reinterpret_cast<uintptr_t>(ws) & 15u) == 0;
-    if (const char* e = std::getenv("SSNT_TONE_BF")) use_bf = use_bf && std::atoi(e) != 0;  // test aid (both kernels are pinned to the same vectors)
-    if (use_bf) only = launch_tone_bf(a, (char*)ws + log_bytes, done_counter_for(ws), stream);
+    const bool aligned = (reinterpret_cast<uintptr_t>(ws) & 15u) == 0;
+    const bool can_bf = tone_bf_supported(a) && aligned, can_ws = tone_ws_supported(a) && aligned;
+    int kind = tone_forced_kernel_kind();
+    if (kind < 0) {
+        if (can_ws && (!can_bf || (size_t)a.batch_size >= (size_t)2 * sm_count())) kind = 2;
+        else kind = can_bf ? 1 : 0;
+    }
+    if ((kind == 1 && !can_bf) || (kind >= 2 && !can_ws)) kind = 0;
+    tone_note_kernel_kind(kind);
+    const size_t bf_bytes = (tone_bf_workspace_bytes(a.batch_size, a.max_t, a.max_u, K) + 255) & ~(size_t)255;
+    if (kind == 1) only = launch_tone_bf(a, (char*)ws + log_bytes, done_counter_for(ws), stream);
+    else if (kind >= 2) only = launch_tone_ws(a, (char*)ws + log_bytes + bf_bytes, kind == 3, stream);
     a.xchg = loss_exchange_device();  // only this kernel's reduction is exchanged (the block-float kernel's is provisional)
     ToneParams p;
     p.a = a;

@@ -361,12 +361,26 @@ def test_auto_dispatch_small_and_large_batches(product):
 # ---- tone-latent lattice: block-float split-role kernel (K = 4, max_u in {32, 64, 128}) ------------------------
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("B,T,U", [(2, 40, 32), (3, 100, 64), (2, 300, 128), (1, 801, 128), (35, 64, 32), (2, 5, 32)])
-@pytest.mark.parametrize("bf", ["1", "0"])
-def test_tone_latent_block_float_and_log_kernels(product, oracle_mod, monkeypatch, B, T, U, bf):
-    """Shapes the block-float tone kernel takes (bf=1) against the fp64 oracle, ragged lengths; bf=0 runs the
-    log-domain kernel on the same inputs (SSNT_TONE_BF=0), so both paths are pinned to the same vectors."""
-    monkeypatch.setenv("SSNT_TONE_BF", bf)
+@pytest.mark.parametrize("kind", [1, 0, 2, 3])
+def test_tone_latent_block_float_and_log_kernels(product, oracle_mod, B, T, U, kind):
+    """Shapes the split-role block-float tone kernel takes (kind 1) against the fp64 oracle, ragged lengths; kind 0 runs
+    the log-domain kernel on the same inputs, kind 2 the warp-serial block-float kernels, kind 3 those with every
+    utterance re-run in the log domain, so all paths are pinned to the same vectors."""
     K = 4
+    _tone_case(product, oracle_mod, B, T, U, K, kind)
+
+
+# ---- tone-latent lattice: warp-serial block-float kernels (K in {2,4,8}, max_u in {32,64,128,256}) -------------
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,T,U,K", [(3, 90, 32, 8), (3, 70, 64, 2), (2, 130, 64, 8), (4, 150, 128, 2), (2, 200, 128, 8),
+                                     (2, 400, 256, 2), (2, 500, 256, 4), (40, 64, 64, 4), (2, 1100, 128, 4)])
+@pytest.mark.parametrize("kind", [2, 3])
+def test_tone_latent_warp_serial_kernels(product, oracle_mod, B, T, U, K, kind):
+    """Every shape family of the warp-serial tone kernels (csrc/tone_ws.cu) against the fp64 oracle, ragged lengths."""
+    _tone_case(product, oracle_mod, B, T, U, K, kind)
+
+
+def _tone_case(product, oracle_mod, B, T, U, K, kind):
     le, ls, lt = make_inputs(B, T, U, seed=T + U, K=K)
     rng = np.random.default_rng(T * 3 + U)
     t_len = rng.integers(max(1, T // 2), T + 1, B).astype(np.int32)
@@ -374,11 +388,18 @@ def test_tone_latent_block_float_and_log_kernels(product, oracle_mod, monkeypatc
     t_len[0] = T
     u_len[0] = min(U, T)
     want = oracle_mod.tone_latent_forward_backward(le, ls, lt, t_len, u_len)
-    got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
-    ll, loss, ge, gs, gt = (_np(g) for g in got)
+    product.set_tone_kernel(kind)
+    try:
+        got = product.tone_latent_forward_backward(_dev(le), _dev(ls), _dev(lt), _dev(t_len), _dev(u_len))
+        ll, loss, ge, gs, gt = (_np(g) for g in got)
+        assert product.tone_kernel_used() == kind
+    finally:
+        product.set_tone_kernel(-1)
     finite = np.isfinite(want[0])
     assert np.array_equal(np.isfinite(ll), finite)
     assert np.all(np.abs(ll[finite] - want[0][finite]) <= LL_RTOL * np.abs(want[0][finite]) + 1e-6)
+    if finite.all():
+        assert abs(float(loss[0]) - want[1]) <= LL_RTOL * max(abs(want[1]), 1.0)
     for b in range(B):
         scale = max(float(np.abs(want[2][b]).max()), 1e-30)
         assert np.abs(ge[b] - want[2][b]).max() <= GRAD_RTOL * scale
