@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(32) fb_log_warp_kernel(const LogParams p) {
     int U = a.u_len ? a.u_len[b] : a.max_u;
     T = min(max(T, 0), a.max_t);
     U = min(max(U, 0), a.max_u);
+    tp_pdl_trigger();           // a following time-parallel call's first kernel may be launched (it waits for this grid)
     if (p.only) tp_pdl_wait();  // launched as a dependent of the time-parallel kernels: wait for their status words
     if (p.only && p.only[b] == 0u) {
         // re-run mode: this utterance's block-float results stand
@@ -407,11 +408,6 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     pg.G = G;
     const TpParams& p2 = pg;
     const bool lg = a.logits != nullptr;  // raw-logit mode: one input tensor, one gradient tensor
-    if (stages >= 1) {
-        if (lg) tp_build_kernel<CPL, L, true><<<tasks, 32, chunk_smem, stream>>>(p2);
-        else tp_build_kernel<CPL, L, false><<<tasks, 32, chunk_smem, stream>>>(p2);
-    }
-    SSNT_CUDA(cudaGetLastError());
     // dependent launches: each kernel's CTAs start while its predecessor drains and block in griddepcontrol.wait
     cudaLaunchAttribute pdl[1];
     pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -419,7 +415,15 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.stream = stream;
     cfg.attrs = pdl;
-    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 5; }();  // tuning aid: 1 combine, 2 fill (measured slower: its 1600 CTAs crowd the combine CTAs), 4 re-run
+    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 5; }();  // tuning aid: 1 combine, 2 fill (measured slower: its 1600 CTAs crowd the combine CTAs), 4 re-run, 8 build as a dependent of the previous call's re-run kernel (measured 1 us slower at cfg2: off)
+    cfg.numAttrs = (pdl_mask & 8) ? 1 : 0;
+    if (stages >= 1) {
+        cfg.gridDim = dim3(tasks);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = chunk_smem;
+        if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, true>, pg));
+        else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, false>, pg));
+    }
     cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
     if (stages >= 2) {
         cfg.gridDim = dim3((unsigned)a.batch_size * 2u);

@@ -172,6 +172,21 @@ __device__ __forceinline__ void tp_issue_chunk(const FbArgs& a, int b, int t0, i
     bulk_g2s(smem_u32(ss), a.log_shift + (size_t)b * slab + (size_t)t0 * a.max_u, bytes, bar);
 }
 
+// The same chunk in kTpLoadStages pieces of L / kTpLoadStages rows, one mbarrier each (bars[0..kTpLoadStages)), so that
+// the first rows can be worked on while the later ones are still in flight (the whole grid issues its loads at once:
+// a chunk's last byte arrives microseconds after its first).  Pieces beyond `rows` are not issued and never awaited.
+constexpr int kTpLoadStages = 4;
+template <int L>
+__device__ __forceinline__ void tp_issue_chunk_staged(const FbArgs& a, int b, int t0, int rows, float* se, float* ss, uint64_t* bars) {
+    static_assert(L % kTpLoadStages == 0, "chunk length must be a multiple of the load stages");
+    constexpr int R = L / kTpLoadStages;
+#pragma unroll
+    for (int s = 0; s < kTpLoadStages; ++s) {
+        const int r = min(R, rows - s * R);
+        if (r > 0) tp_issue_chunk(a, b, t0 + s * R, r, se + s * R * a.max_u, ss + s * R * a.max_u, smem_u32(bars + s));
+    }
+}
+
 __device__ __forceinline__ bool tp_lengths(const FbArgs& a, int b, int& T, int& U) {
     T = a.t_len ? a.t_len[b] : a.max_t;
     U = a.u_len ? a.u_len[b] : a.max_u;
@@ -198,11 +213,16 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* se = reinterpret_cast<float*>(smem_raw + 128);
     float* ss = se + L * max_u;
+    const int rows = min(L, a.max_t - t0);
     if (lane == 0) {
-        mbar_init(smem_u32(bar), 1);
+        for (int s = 0; s < kTpLoadStages; ++s) mbar_init(smem_u32(bar + s), 1);
         fence_mbar_init();
-        tp_issue_chunk(a, b, t0, min(L, a.max_t - t0), se, ss, smem_u32(bar));
     }
+    // This grid is itself launched as a programmatic dependent of whatever precedes it in the stream (normally the
+    // previous call's re-run kernel, which triggers at its start): everything above overlaps that kernel's tail; the
+    // inputs may only be read and the workspace only be written once it has completed.
+    tp_pdl_wait();
+    if (lane == 0) tp_issue_chunk_staged<L>(a, b, t0, rows, se, ss, bar);
     __syncwarp();
     const int c0 = lane * CPL;
     const int src = (lane + 31) & 31;  // left neighbour, lane 0 wraps to lane 31 whose last shift is always 0
@@ -214,9 +234,9 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
 #pragma unroll
         for (int d = 1; d <= L; ++d) Q[r][d] = 0.0f;
     }
-    tp_wait(smem_u32(bar), 0, 1);
 #pragma unroll
     for (int l = 0; l < L; ++l) {
+        if (l % (L / kTpLoadStages) == 0 && l < rows) tp_wait(smem_u32(bar + l / (L / kTpLoadStages)), 0, 1);
         float e[CPL], s[CPL];
         if constexpr (LG) {
             float pu[CPL], qu[CPL];
@@ -504,10 +524,11 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* se = reinterpret_cast<float*>(smem_raw + 128);
     float* ss = se + L * max_u;
+    const int rows = min(L, max_t - t0);
     if (lane == 0) {
-        mbar_init(smem_u32(bar), 1);
+        for (int s = 0; s < kTpLoadStages; ++s) mbar_init(smem_u32(bar + s), 1);
         fence_mbar_init();
-        tp_issue_chunk(a, b, t0, min(L, max_t - t0), se, ss, smem_u32(bar));
+        tp_issue_chunk_staged<L>(a, b, t0, rows, se, ss, bar);
     }
     __syncwarp();
     if (c == 0 && lane == 0) {
@@ -575,11 +596,11 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
         sb = ex2(fminf(fmaxf(half, -126.0f), 126.0f));
     }
 
-    tp_wait(smem_u32(bar), 0, 3);
     // ---- alpha forward: rows 0..L-1 of the chunk kept in registers (scaled by sa); probabilities written back ----
     float ar[L][CPL];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
+        if (l % (L / kTpLoadStages) == 0 && l < rows) tp_wait(smem_u32(bar + l / (L / kTpLoadStages)), 0, 3);
         float e[CPL], s[CPL];
         if constexpr (LG) {  // the UNMASKED pair goes back to shared memory: the beta sweep chains the gradient through it
             float pu[CPL], qu[CPL];
