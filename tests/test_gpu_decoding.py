@@ -71,6 +71,33 @@ def test_edit_distance_random(product, oracle_mod, space, B, L, vocab):
     _eq(got, want)
 
 
+@pytest.mark.parametrize("L", [31, 32, 33, 64, 65, 96, 257, 1023, 1024, 1025])
+def test_edit_distance_block_edges(product, oracle_mod, space, L):
+    """The bit-parallel kernel cuts sequence a into 32-row blocks, one per lane (max_length <= 1024; 1025 takes the
+    wavefront kernel): lengths on either side of every block edge, identical / disjoint / shifted pairs, a two-symbol
+    alphabet and arbitrary int32 symbols (negative, large) — bit-exact against src/edit_distance.rs:6-60."""
+    rng = np.random.default_rng(L)
+    lens = sorted({0, 1, 2, 31, 32, 33, 63, 64, 65, L // 2, L - 33, L - 32, L - 31, L - 1, L} & set(range(L + 1)))
+    pairs = [(m, n) for m in lens for n in lens]
+    pairs = [pairs[i] for i in rng.permutation(len(pairs))[:48]] + [(L, L), (L, 1), (1, L), (L, L), (L, L), (L, L)]
+    B = len(pairs)
+    a = rng.integers(0, 2, (B, L)).astype(np.int32)
+    b = rng.integers(0, 2, (B, L)).astype(np.int32)
+    wide = rng.integers(-2**31, 2**31 - 1, (B, L), dtype=np.int64).astype(np.int32)
+    a[8:16] = wide[8:16]
+    b[8:16] = np.where(rng.random((8, L)) < 0.2, wide[16:24], wide[8:16])
+    a[-3], b[-3] = 7, 7                       # identical: 0
+    a[-2], b[-2] = np.arange(L), np.arange(L) + L   # disjoint: L
+    a[-1] = rng.integers(0, 5, L)
+    b[-1] = np.roll(a[-1], 3)                 # shifted by three
+    al = np.array([m for m, _ in pairs], np.int32)
+    bl = np.array([n for _, n in pairs], np.int32)
+    want = oracle_mod.levenshtein_edit_distance(a, b, al, bl)
+    assert want[-3] == 0 and want[-2] == L
+    got = product.levenshtein_edit_distance(*_conv(space, a, b, al, bl))
+    _eq(got, want)
+
+
 # ---------------------------------------------------------------- back-trace / upsample
 def test_extract_best_beam_branch_golden(product, space):
     bb, th = _conv(space, G.BACKTRACE_TABLE, G.BACKTRACE_TABLE)
