@@ -386,16 +386,21 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     const FbArgs& a = p.a;
     const size_t chunk_smem = 128 + (size_t)2 * L * a.max_u * sizeof(float);
     constexpr int NT = 32 * CPL;
-    constexpr int NS = NT <= 128 ? 16 : 8;   // 139 KB of operators in flight per (utterance, direction)
+    constexpr int NS0 = NT <= 128 ? 16 : 8;   // 139 KB of operators in flight per (utterance, direction)
+    // tuning aid: half the ring (leaves room for more early-launched fill CTAs next to a combine CTA)
+    static const int ring_sel = [] { const char* e = std::getenv("SSNT_TP_RING"); return e ? std::atoi(e) : 0; }();  // 1 half, 2 one and a half
+    const int NS = ring_sel == 1 ? NS0 / 2 : (ring_sel == 2 ? NS0 * 3 / 2 : NS0);
     // Exponent granularity of the boundary vectors (G): a warp's 32 tokens for short sweeps of narrow lattices, half a
     // warp otherwise — long sweeps lose likelihood with 32-token groups (T = 2000 at U = 256: ~1e-4; T = 1000 at U = 128:
     // 5 of 1184 random utterances missed the 3e-5 agreement of the two sweeps and were re-run), see the call sites.
-    const size_t ring_smem = 512 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
+    const size_t ring_smem = 576 + ((size_t)2 * (2 * L + NT) + 4) * sizeof(float) + (size_t)NS * (L + 1) * NT * sizeof(float);
     static size_t configured_[64] = {};  // per device
     size_t& configured = configured_[device_ordinal()];
     if (configured == 0) configured = 48 * 1024;
     if (ring_smem > configured) {
-        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS0, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS0 / 2, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        SSNT_CUDA(cudaFuncSetAttribute(tp_combine_kernel<NT, L, NS0 * 3 / 2, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
         configured = ring_smem;
     }
     const unsigned tasks = (unsigned)a.batch_size * (unsigned)p.C;
@@ -415,7 +420,7 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.stream = stream;
     cfg.attrs = pdl;
-    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 5; }();  // tuning aid: 1 combine, 2 fill (measured slower: its 1600 CTAs crowd the combine CTAs), 4 re-run, 8 build as a dependent of the previous call's re-run kernel (measured 1 us slower at cfg2: off)
+    static const int pdl_mask = [] { const char* e = std::getenv("SSNT_TP_PDL"); return e ? std::atoi(e) : 7; }();  // tuning aid: 1 combine, 2 fill (its row conversions run before it waits: 0.9 us at cfg2, 3.5 us at B=148), 4 re-run, 8 build as a dependent of the previous call's re-run kernel (measured 1 us slower at cfg2: off)
     cfg.numAttrs = (pdl_mask & 8) ? 1 : 0;
     if (stages >= 1) {
         cfg.gridDim = dim3(tasks);
@@ -429,7 +434,9 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.gridDim = dim3((unsigned)a.batch_size * 2u);
         cfg.blockDim = dim3(NT + 32);
         cfg.dynamicSmemBytes = ring_smem;
-        SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_combine_kernel<NT, L, NS, G>, pg));
+        if (ring_sel == 1) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_combine_kernel<NT, L, NS0 / 2, G>, pg));
+        else if (ring_sel == 2) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_combine_kernel<NT, L, NS0 * 3 / 2, G>, pg));
+        else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_combine_kernel<NT, L, NS0, G>, pg));
     }
     cfg.numAttrs = (pdl_mask & 2) ? 1 : 0;
     if (stages >= 3) {

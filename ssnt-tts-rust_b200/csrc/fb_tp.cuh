@@ -344,7 +344,7 @@ __device__ __forceinline__ void tp_combine_sweep(const TpParams& p, int b, int U
         const int Fnk = fsm[(k & 3) * 16 + wnc];
         const int Fn2k = fsm[(k & 3) * 16 + wn2c];
         const int Fnk1 = fsm[((k + 1) & 3) * 16 + wnc];
-        const float* q = qbase + (size_t)(k & (NS - 1)) * stage_floats;
+        const float* q = qbase + (size_t)(k % NS) * stage_floats;
         const float* yv = ybase + cur * VB;
         float yw[L + 1], qw[L + 1];
 #pragma unroll
@@ -421,7 +421,7 @@ template <int NT, int L, int NS, int G>
 __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     static_assert(L <= G && (G == 16 || G == 32), "a window must not reach beyond the neighbouring exponent group");
-    static_assert((NS & (NS - 1)) == 0 && NS <= 16, "ring size: power of two");
+    static_assert(NS >= 2 && NS <= 24, "ring size");
     constexpr int VB = L + NT + L;  // one padded vector
     constexpr int stage_floats = (L + 1) * NT;
     const FbArgs& a = p.a;
@@ -431,10 +431,10 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
     if (!tp_lengths(a, b, T, U)) return;
     if (dir == 0 && tid == 0) p.status[b] = 0u;  // the fill kernel ORs into it
     const int Cb = (T + L - 1) / L;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                  // [NS]
-    unsigned* wmax = reinterpret_cast<unsigned*>(smem_raw + 128);            // [2][16] group maxima (float bits)
-    int* fsm = reinterpret_cast<int*>(smem_raw + 256);                       // [4][16] group frames of vectors k..k+3 (mod 4)
-    float* vbuf = reinterpret_cast<float*>(smem_raw + 512);                  // [2][VB]
+    unsigned* wmax = reinterpret_cast<unsigned*>(smem_raw);                  // [2][16] group maxima (float bits)
+    int* fsm = reinterpret_cast<int*>(smem_raw + 128);                       // [4][16] group frames of vectors k..k+3 (mod 4)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 384);            // [NS <= 24]
+    float* vbuf = reinterpret_cast<float*>(smem_raw + 576);                  // [2][VB]
     float* ring = vbuf + 2 * VB + ((4 - (2 * VB) % 4) % 4);                  // 16-byte aligned
     const bool producer = tid >= NT;
     tp_pdl_trigger();  // the fill kernel's CTAs may be launched (they wait for this grid's completion before reading)
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
         const float* qb = p.Q + (size_t)b * p.C * stage_floats;
         auto issue = [&](int k) {
             const int ck = dir == 0 ? k : Cb - 1 - k;
-            const int slot = k & (NS - 1);
+            const int slot = k % NS;
             const uint32_t bar = smem_u32(bars + slot);
             mbar_expect_tx(bar, (uint32_t)stage_floats * 4u);
             bulk_g2s(smem_u32(ring + (size_t)slot * stage_floats), qb + (size_t)ck * stage_floats, (uint32_t)stage_floats * 4u, bar);
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
         for (int k = 0; k < Cb; ++k) {
             __syncthreads();  // B_k: every compute warp is done with stage k-1
             if (lane == 0 && k >= 1 && k - 1 + NS < Cb) issue(k - 1 + NS);
-            if (k + 1 < Cb && !(p.debug & 4)) tp_wait(smem_u32(bars + ((k + 1) & (NS - 1))), (unsigned)((k + 1) / NS) & 1u, 2);
+            if (k + 1 < Cb && !(p.debug & 4)) tp_wait(smem_u32(bars + ((k + 1) % NS)), (unsigned)((k + 1) / NS) & 1u, 2);
         }
         return;
     }
@@ -495,15 +495,46 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     int T, U;
     const int rows_end = min(t0 + L, max_t);
     tp_pdl_trigger();  // the log-domain re-run kernel may be launched; it waits for this grid before reading status
-    tp_pdl_wait();     // the combine kernel has completed: boundary vectors, likelihoods and status are visible
-    if (!tp_lengths(a, b, T, U)) {
+    // This grid may itself be launched as a programmatic dependent of the combine kernel (tuning mask bit 2): everything
+    // up to tp_pdl_wait() touches only the call's inputs and gradient outputs (the build kernel, a full dependency of
+    // whatever preceded the call, has completed), never what the combine kernel writes.
+    const bool feasible = tp_lengths(a, b, T, U);
+    if (!feasible || t0 >= T) {
         zero_rows(t0, rows_end);
-        if (c == 0 && lane == 0) {
+        if (!feasible && c == 0 && lane == 0) {
+            tp_pdl_wait();  // the combine kernel writes nothing for such an utterance, but keep the order of the status writes
             a.log_likelihood[b] = -INFINITY;
             p.status[b] = 0u;
         }
         return;
     }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* se = reinterpret_cast<float*>(smem_raw + 128);
+    float* ss = se + L * max_u;
+    const int rows = min(L, max_t - t0);
+    if (lane == 0) {
+        for (int s = 0; s < kTpLoadStages; ++s) mbar_init(smem_u32(bar + s), 1);
+        fence_mbar_init();
+        tp_issue_chunk_staged<L>(a, b, t0, rows, se, ss, bar);
+    }
+    __syncwarp();
+    // ---- the chunk's rows as probabilities, in place (each lane re-reads only what it wrote itself) ----
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        if (l % (L / kTpLoadStages) == 0 && l < rows) tp_wait(smem_u32(bar + l / (L / kTpLoadStages)), 0, 3);
+        float e[CPL], s[CPL];
+        if constexpr (LG) {  // the UNMASKED pair: the beta sweep chains the gradient through it; masks are applied on use
+            float pu[CPL], qu[CPL];
+            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+            store_cells<CPL>(se + l * max_u, c0, max_u, pu);
+            store_cells<CPL>(ss + l * max_u, c0, max_u, qu);
+        } else {
+            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+            store_cells<CPL>(se + l * max_u, c0, max_u, e);
+            store_cells<CPL>(ss + l * max_u, c0, max_u, s);
+        }
+    }
+    tp_pdl_wait();     // the combine kernel has completed: boundary vectors, likelihoods and status are visible
     // the two sweeps' likelihoods: (log2 mantissa, exponent)
     const float* z = p.zlg + (size_t)b * 4;
     const float zf_lg = z[0], zf_ex = z[1], zb_lg = z[2], zb_ex = z[3];
@@ -517,20 +548,6 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #endif
         return;
     }
-    if (t0 >= T) {
-        zero_rows(t0, rows_end);
-        return;
-    }
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* se = reinterpret_cast<float*>(smem_raw + 128);
-    float* ss = se + L * max_u;
-    const int rows = min(L, max_t - t0);
-    if (lane == 0) {
-        for (int s = 0; s < kTpLoadStages; ++s) mbar_init(smem_u32(bar + s), 1);
-        fence_mbar_init();
-        tp_issue_chunk_staged<L>(a, b, t0, rows, se, ss, bar);
-    }
-    __syncwarp();
     if (c == 0 && lane == 0) {
         a.log_likelihood[b] = (float)(((double)zf_lg + (double)zf_ex) * kLn2);
         // status[b] was zeroed by the combine kernel; a bad row below ORs into it
@@ -596,21 +613,21 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
         sb = ex2(fminf(fmaxf(half, -126.0f), 126.0f));
     }
 
-    // ---- alpha forward: rows 0..L-1 of the chunk kept in registers (scaled by sa); probabilities written back ----
+    // ---- alpha forward: rows 0..L-1 of the chunk kept in registers (scaled by sa) ----
     float ar[L][CPL];
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-        if (l % (L / kTpLoadStages) == 0 && l < rows) tp_wait(smem_u32(bar + l / (L / kTpLoadStages)), 0, 3);
         float e[CPL], s[CPL];
-        if constexpr (LG) {  // the UNMASKED pair goes back to shared memory: the beta sweep chains the gradient through it
-            float pu[CPL], qu[CPL];
-            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
-            store_cells<CPL>(se + l * max_u, c0, max_u, pu);
-            store_cells<CPL>(ss + l * max_u, c0, max_u, qu);
-        } else {
-            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
-            store_cells<CPL>(se + l * max_u, c0, max_u, e);  // the raw rows are overwritten in place by the probabilities
-            store_cells<CPL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
+        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
+        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+        if constexpr (LG) {  // sigmoid(+-z) as stored above; the lattice's masks are applied here
+            const int t = t0 + l;
+            const bool last = t == T - 1;
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                e[r] = t < T ? ((c0 + r < U) ? e[r] : 0.0f) : 1.0f;
+                s[r] = (t < T && c0 + r < U - 1 && !last) ? s[r] : 0.0f;
+            }
         }
 #pragma unroll
         for (int r = 0; r < CPL; ++r) ar[l][r] = av[r] * sa;
