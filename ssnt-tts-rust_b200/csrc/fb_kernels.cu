@@ -413,6 +413,9 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     pg.G = G;
     const TpParams& p2 = pg;
     const bool lg = a.logits != nullptr;  // raw-logit mode: one input tensor, one gradient tensor
+    // every lane's cells exist (max_u = 32 * CPL: 64, 128, 256): chunk kernels without bounds checks on their row accesses
+    static const bool no_full = [] { const char* e = std::getenv("SSNT_TP_NO_FULL"); return e && std::atoi(e) != 0; }();  // A/B aid
+    const bool full = a.max_u == 32 * CPL && p.UP == 32 * CPL && !no_full;
     // dependent launches: each kernel's CTAs start while its predecessor drains and block in griddepcontrol.wait
     cudaLaunchAttribute pdl[1];
     pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -427,6 +430,7 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.blockDim = dim3(32);
         cfg.dynamicSmemBytes = chunk_smem;
         if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, true>, pg));
+        else if (full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, false, true>, pg));
         else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, false>, pg));
     }
     cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
@@ -444,6 +448,7 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.blockDim = dim3(32);
         cfg.dynamicSmemBytes = chunk_smem;
         if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, true>, pg));
+        else if (full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, false, true>, pg));
         else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, false>, pg));
     }
 }

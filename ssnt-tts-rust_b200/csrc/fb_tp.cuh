@@ -104,21 +104,77 @@ __device__ __forceinline__ void tp_store(float* p, const float (&v)[CPL]) {
     }
 }
 
+// Row accesses of the chunk kernels.  FULL: max_u == 32 * CPL, every lane's cells exist — plain 128-bit accesses, no
+// bounds check (the checked form costs a branch with a reconvergence point per access, ~20 % of the fill kernel's
+// instructions); otherwise the checked helpers of lattice_common.cuh.
+template <int CPL, bool FULL>
+__device__ __forceinline__ void tp_ld(const float* row, int c0, int max_u, float (&v)[CPL]) {
+    if constexpr (FULL) tp_load<CPL>(row + c0, v);
+    else load_cells<CPL>(row, c0, max_u, 0.0f, v);
+}
+template <int CPL, bool FULL>
+__device__ __forceinline__ void tp_st(float* row, int c0, int max_u, const float (&v)[CPL]) {
+    if constexpr (FULL) tp_store<CPL>(row + c0, v);
+    else store_cells<CPL>(row, c0, max_u, v);
+}
+template <int CPL, bool FULL>
+__device__ __forceinline__ void tp_st_cs(float* row, int c0, int max_u, const float (&v)[CPL]) {
+    if constexpr (FULL) {
+        if constexpr (CPL >= 4) {
+#pragma unroll
+            for (int q = 0; q < CPL / 4; ++q)
+                __stcs(reinterpret_cast<float4*>(row + c0 + 4 * q), make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        } else {
+            __stcs(reinterpret_cast<float2*>(row + c0), make_float2(v[0], v[1]));
+        }
+    } else {
+        store_cells_cs<CPL>(row, c0, max_u, v);
+    }
+}
+
+// Sums N per-lane values over the 32 lanes, N values at once: at every butterfly level a lane keeps one half of the
+// values and hands the other half to its partner, so the N sums cost N - 1 + (levels left) shuffles instead of 5 N and
+// sit on no dependency chain.  On return v[0] holds the complete sum of ONE of the N values (which one depends on the
+// lane; every value is held by 32 / N lanes).
+template <int N>
+__device__ __forceinline__ void tp_sum_many(float (&v)[N], int lane) {
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "power of two");
+    int n = N;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        if (n > 1) {
+            const bool hi = (lane & o) != 0;
+            const int h = n / 2;
+#pragma unroll
+            for (int i = 0; i < N / 2; ++i) {
+                if (i < h) {
+                    const float send = hi ? v[i] : v[i + h];
+                    const float keep = hi ? v[i + h] : v[i];
+                    v[i] = keep + __shfl_xor_sync(kFull, send, o);
+                }
+            }
+            n = h;
+        } else {
+            v[0] += __shfl_xor_sync(kFull, v[0], o);
+        }
+    }
+}
+
 // One lattice row of a chunk as probabilities, from the raw log-prob rows in shared memory.
 // Frames t >= T act as the identity (e = 1, s = 0) so that the virtual terminal vector passes through
 // a partial last chunk unchanged; tokens >= U and the prohibited shifts (last token, last frame) are 0.
-template <int CPL>
+template <int CPL, bool FULL = false>
 __device__ __forceinline__ void tp_row_probs(const float* se, const float* ss, int l, int t, int T, int U, int max_u,
                                              int c0, float (&e)[CPL], float (&s)[CPL]) {
     if (t < T) {
         float re[CPL], rs[CPL];
-        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, re);
-        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, rs);
+        tp_ld<CPL, FULL>(se + l * max_u, c0, max_u, re);
+        tp_ld<CPL, FULL>(ss + l * max_u, c0, max_u, rs);
         const bool last = t == T - 1;
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
-            e[r] = (c0 + r < U) ? ex2(to_log2(re[r])) : 0.0f;
-            s[r] = (c0 + r < U - 1 && !last) ? ex2(to_log2(rs[r])) : 0.0f;
+            e[r] = (c0 + r < U) ? ex2(re[r] * kLog2e) : 0.0f;   // ex2(-inf) = 0: no clamp needed (same bits as ex2(to_log2(.)))
+            s[r] = (c0 + r < U - 1 && !last) ? ex2(rs[r] * kLog2e) : 0.0f;
         }
     } else {
 #pragma unroll
@@ -139,12 +195,12 @@ __device__ __forceinline__ void sigmoid_pair(float z, float& p, float& q) {
 
 // Raw-logit mode: one lattice row as probabilities from the logit row in shared memory; (e, s) carry the lattice's
 // masks like tp_row_probs, (pu, qu) are the unmasked sigmoid(z), sigmoid(-z) the gradient is chained through.
-template <int CPL>
+template <int CPL, bool FULL = false>
 __device__ __forceinline__ void tp_row_probs_logits(const float* sz, int l, int t, int T, int U, int max_u, int c0,
                                                     float (&e)[CPL], float (&s)[CPL], float (&pu)[CPL], float (&qu)[CPL]) {
     if (t < T) {
         float rz[CPL];
-        load_cells<CPL>(sz + l * max_u, c0, max_u, 0.0f, rz);
+        tp_ld<CPL, FULL>(sz + l * max_u, c0, max_u, rz);
         const bool last = t == T - 1;
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
@@ -198,7 +254,7 @@ __device__ __forceinline__ bool tp_lengths(const FbArgs& a, int b, int& T, int& 
 // =================================================================================================
 // Kernel 1: chunk operators.
 // =================================================================================================
-template <int CPL, int L, bool LG = false>
+template <int CPL, int L, bool LG = false, bool FULL = false>
 __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FbArgs& a = p.a;
@@ -209,7 +265,7 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
     if (!tp_lengths(a, b, T, U)) return;
     const int t0 = c * L;
     if (t0 >= T) return;
-    const int max_u = a.max_u;
+    const int max_u = FULL ? 32 * CPL : a.max_u;  // FULL: a compile-time constant
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     float* se = reinterpret_cast<float*>(smem_raw + 128);
     float* ss = se + L * max_u;
@@ -240,9 +296,9 @@ __global__ void __launch_bounds__(32) tp_build_kernel(const TpParams p) {
         float e[CPL], s[CPL];
         if constexpr (LG) {
             float pu[CPL], qu[CPL];
-            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+            tp_row_probs_logits<CPL, FULL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
         } else {
-            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+            tp_row_probs<CPL, FULL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
         }
         // what enters this lane's first token from the left neighbour's last token, per diagonal
         float X[L];
@@ -473,13 +529,13 @@ __global__ void __launch_bounds__(NT + 32) tp_combine_kernel(const TpParams p) {
 // =================================================================================================
 // Kernel 3: chunk interiors and gradients.
 // =================================================================================================
-template <int CPL, int L, bool LG = false>
+template <int CPL, int L, bool LG = false, bool FULL = false>
 __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FbArgs& a = p.a;
     const int lane = threadIdx.x;
     const int b = blockIdx.x / p.C, c = blockIdx.x % p.C;
-    const int max_u = a.max_u, max_t = a.max_t, UP = p.UP;
+    const int max_u = FULL ? 32 * CPL : a.max_u, max_t = a.max_t, UP = FULL ? 32 * CPL : p.UP;
     const int c0 = lane * CPL;
     const int t0 = c * L;
     const size_t slab = (size_t)max_t * max_u;
@@ -488,8 +544,8 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     const float zeros[CPL] = {};
     auto zero_rows = [&](int from, int to) {
         for (int t = from; t < to; ++t) {
-            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-            if constexpr (!LG) store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+            if constexpr (!LG) tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, zeros);
         }
     };
     int T, U;
@@ -525,13 +581,13 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
         float e[CPL], s[CPL];
         if constexpr (LG) {  // the UNMASKED pair: the beta sweep chains the gradient through it; masks are applied on use
             float pu[CPL], qu[CPL];
-            tp_row_probs_logits<CPL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
-            store_cells<CPL>(se + l * max_u, c0, max_u, pu);
-            store_cells<CPL>(ss + l * max_u, c0, max_u, qu);
+            tp_row_probs_logits<CPL, FULL>(se, l, t0 + l, T, U, max_u, c0, e, s, pu, qu);
+            tp_st<CPL, FULL>(se + l * max_u, c0, max_u, pu);
+            tp_st<CPL, FULL>(ss + l * max_u, c0, max_u, qu);
         } else {
-            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
-            store_cells<CPL>(se + l * max_u, c0, max_u, e);
-            store_cells<CPL>(ss + l * max_u, c0, max_u, s);
+            tp_row_probs<CPL, FULL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+            tp_st<CPL, FULL>(se + l * max_u, c0, max_u, e);
+            tp_st<CPL, FULL>(ss + l * max_u, c0, max_u, s);
         }
     }
     tp_pdl_wait();     // the combine kernel has completed: boundary vectors, likelihoods and status are visible
@@ -618,8 +674,8 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
         float e[CPL], s[CPL];
-        load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
-        load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+        tp_ld<CPL, FULL>(se + l * max_u, c0, max_u, e);
+        tp_ld<CPL, FULL>(ss + l * max_u, c0, max_u, s);
         if constexpr (LG) {  // sigmoid(+-z) as stored above; the lattice's masks are applied here
             const int t = t0 + l;
             const bool last = t == T - 1;
@@ -640,14 +696,14 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
     }
     __syncwarp();
     // ---- beta backward with the gradients fused ----
-    float worst = 0.0f;
+    float rsum[L];  // per-lane share of every row's occupancy sum; the sums are formed after the sweep
 #pragma unroll
     for (int l = L - 1; l >= 0; --l) {
         const int t = t0 + l;
         float e[CPL], s[CPL], pu[CPL], qu[CPL];
         if constexpr (LG) {  // sigmoid(+-z) as stored by the alpha sweep; the lattice's masks are re-applied here
-            load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, pu);
-            load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, qu);
+            tp_ld<CPL, FULL>(se + l * max_u, c0, max_u, pu);
+            tp_ld<CPL, FULL>(ss + l * max_u, c0, max_u, qu);
             const bool last = t == T - 1;
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
@@ -655,8 +711,8 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
                 s[r] = (t < T && c0 + r < U - 1 && !last) ? qu[r] : 0.0f;
             }
         } else {
-            load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
-            load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+            tp_ld<CPL, FULL>(se + l * max_u, c0, max_u, e);
+            tp_ld<CPL, FULL>(ss + l * max_u, c0, max_u, s);
         }
         const float bin = __shfl_down_sync(kFull, bv[0], 1) * kb;
         float g1[CPL], g2[CPL];
@@ -675,23 +731,28 @@ __global__ void __launch_bounds__(32) tp_fill_kernel(const TpParams p) {
                 float gz[CPL];
 #pragma unroll
                 for (int r = 0; r < CPL; ++r) gz[r] = g1[r] * qu[r] - g2[r] * pu[r];
-                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, gz);
+                tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, gz);
             } else {
-                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
-                store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+                tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, g1);
+                tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, g2);
             }
-            rowsum = warp_sum(rowsum);
-            const float dev = fabsf(rowsum - 1.0f);
-            worst = (dev <= kTpRowTol) ? worst : 1.0f;  // also catches NaN
-#ifdef SSNT_TP_TRACE
-            if (!(dev <= kTpRowTol) && lane == 0) printf("tp: b=%d t=%d row sum %g (fa %d fb %d sa %g sb %g)\n", b, t, rowsum, fa, fb, sa, sb);
-#endif
-        } else if (t < max_t) {
-            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-            if constexpr (!LG) store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            rsum[l] = rowsum;
+        } else {
+            rsum[l] = lane == 0 ? 1.0f : 0.0f;  // a frame beyond the utterance: nothing to check
+            if (t < max_t) {
+                tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+                if constexpr (!LG) tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            }
         }
     }
-    if (worst != 0.0f && lane == 0) atomicOr(p.status + b, (unsigned)kTpBadRow);
+    // every frame's occupancies must sum to 1
+    tp_sum_many<L>(rsum, lane);
+    const float dev = fabsf(rsum[0] - 1.0f);
+    const bool bad = !(dev <= kTpRowTol);  // also catches NaN
+#ifdef SSNT_TP_TRACE
+    if (bad) printf("tp: b=%d chunk %d lane %d: a row sum is %g (fa %d fb %d sa %g sb %g)\n", b, c, lane, rsum[0], fa, fb, sa, sb);
+#endif
+    if (__any_sync(kFull, bad) && lane == 0) atomicOr(p.status + b, (unsigned)kTpBadRow);
 }
 
 }  // namespace lattice
