@@ -464,6 +464,7 @@ void launch_ws(const WsParams& p, cudaStream_t stream) {
     if (!configured) {
         SSNT_CUDA(cudaFuncSetAttribute(ws_forward_kernel<CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         SSNT_CUDA(cudaFuncSetAttribute(ws_backward_kernel<CPL, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SSNT_CUDA(cudaFuncSetAttribute(ws_backward_kernel<CPL, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
     ws_forward_kernel<CPL, L><<<(unsigned)a.batch_size, 32, fwd_smem, stream>>>(p);
@@ -478,7 +479,10 @@ void launch_ws(const WsParams& p, cudaStream_t stream) {
     cfg.gridDim = dim3((unsigned)a.batch_size);
     cfg.blockDim = dim3(32);
     cfg.dynamicSmemBytes = bwd_smem;
-    SSNT_CUDA(cudaLaunchKernelEx(&cfg, ws_backward_kernel<CPL, L>, p));
+    // every lane's cells exist (max_u = 32 * CPL): no bounds checks on the row accesses, compile-time strides
+    static const bool no_full = [] { const char* e = std::getenv("SSNT_TP_NO_FULL"); return e && std::atoi(e) != 0; }();  // A/B aid
+    if (a.max_u == 32 * CPL && p.UP == 32 * CPL && !no_full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, ws_backward_kernel<CPL, L, true>, p));
+    else SSNT_CUDA(cudaLaunchKernelEx(&cfg, ws_backward_kernel<CPL, L>, p));
 }
 
 }  // namespace

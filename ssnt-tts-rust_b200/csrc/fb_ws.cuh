@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(32) ws_forward_kernel(const WsParams p) {
 // =================================================================================================
 // Backward: chunk by chunk from the end; alpha re-run from the checkpoint, beta with the gradients fused.
 // =================================================================================================
-template <int CPL, int L>
+template <int CPL, int L, bool FULL = false>
 __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FbArgs& a = p.a;
     const int lane = threadIdx.x, b = blockIdx.x;
-    const int max_u = a.max_u, max_t = a.max_t, UP = p.UP;
+    const int max_u = FULL ? 32 * CPL : a.max_u, max_t = a.max_t, UP = FULL ? 32 * CPL : p.UP;  // FULL: every lane's cells exist
     const int c0 = lane * CPL;
     const size_t slab = (size_t)max_t * max_u;
     float* ge = a.grad_emit + (size_t)b * slab;
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
     const float zeros[CPL] = {};
     auto zero_rows = [&](int from, int to) {
         for (int t = from; t < to; ++t) {
-            store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-            store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+            tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+            tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, zeros);
         }
     };
     tp_pdl_trigger();  // the log-domain re-run kernel may be launched; it waits for this grid before reading status
@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
 #pragma unroll
         for (int l = 0; l < L; ++l) {
             float e[CPL], s[CPL];
-            tp_row_probs<CPL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
-            store_cells<CPL>(se + l * max_u, c0, max_u, e);  // raw rows overwritten in place by the probabilities
-            store_cells<CPL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
+            tp_row_probs<CPL, FULL>(se, ss, l, t0 + l, T, U, max_u, c0, e, s);
+            tp_st<CPL, FULL>(se + l * max_u, c0, max_u, e);  // raw rows overwritten in place by the probabilities
+            tp_st<CPL, FULL>(ss + l * max_u, c0, max_u, s);  // (each lane re-reads only what it wrote itself)
 #pragma unroll
             for (int r = 0; r < CPL; ++r) ar[l][r] = av[r] * sa;
             if (l < L - 1) {
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
         for (int l = L - 1; l >= 0; --l) {
             const int t = t0 + l;
             float e[CPL], s[CPL];
-            load_cells<CPL>(se + l * max_u, c0, max_u, 0.0f, e);
-            load_cells<CPL>(ss + l * max_u, c0, max_u, 0.0f, s);
+            tp_ld<CPL, FULL>(se + l * max_u, c0, max_u, e);
+            tp_ld<CPL, FULL>(ss + l * max_u, c0, max_u, s);
             const float bin = __shfl_down_sync(kFull, bv[0], 1) * kb;
             float g1[CPL], g2[CPL];
             float rowsum = 0.0f;
@@ -315,14 +315,14 @@ __global__ void __launch_bounds__(32) ws_backward_kernel(const WsParams p) {
                 bv[r] = p1 + p2;
             }
             if (t < T) {
-                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, g1);
-                store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, g2);
+                tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, g1);
+                tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, g2);
                 // every frame's occupancies sum to 1: accumulated per lane, checked once per chunk below
                 csum += rowsum;
                 ++crows;
             } else if (t < max_t) {
-                store_cells_cs<CPL>(ge + (size_t)t * max_u, c0, max_u, zeros);
-                store_cells_cs<CPL>(gs + (size_t)t * max_u, c0, max_u, zeros);
+                tp_st_cs<CPL, FULL>(ge + (size_t)t * max_u, c0, max_u, zeros);
+                tp_st_cs<CPL, FULL>(gs + (size_t)t * max_u, c0, max_u, zeros);
             }
         }
         // the chunk's occupancies sum to its number of frames (one reduction per chunk instead of one per frame)
