@@ -13,6 +13,8 @@
 //  * kind 0  fb_generic_kernel        any shape/alignment (max_u % 4 != 0, U > 1024, unaligned
 //            bases): one CTA per utterance, one thread per token, rows in shared memory, log2
 //            domain with one integer offset per token.
+#include <algorithm>
+#include <cmath>
 #include "fb_split.cuh"
 #include "fb_tp.cuh"
 #include "fb_ws.cuh"
@@ -453,12 +455,41 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
     }
 }
 
+// Resident warps per SM for the warp-serial kernels.  All utterances of a wave finish together, so what counts is how
+// evenly the batch divides into waves: efficiency(r) = per_sm / (ceil(per_sm / r) * r).  The count that fits is kept
+// unless it wastes more than 30 % of its slots and a smaller one (not below half) is clearly more even.
+inline int ws_resident_cap(size_t batch, int sms, int fit) {
+    if (fit < 4) return fit;
+    const double per_sm = (double)batch / (double)sms;
+    if (per_sm <= (double)fit) return fit;  // one wave anyway
+    auto eff = [&](int r) { return per_sm / (std::ceil(per_sm / r) * r); };
+    const double e0 = eff(fit);
+    if (e0 >= 0.7) return fit;  // measured: switching pays at 0.53 and 0.65 (B = 2048, 2500: +20 %), costs 3-10 % at 0.71-0.78
+    int best = fit;
+    double best_e = e0 + 0.1;
+    for (int r = fit - 1; r >= (fit + 1) / 2 && r >= 4; --r)
+        if (eff(r) > best_e) { best_e = eff(r); best = r; }
+    return best;
+}
+
 // Warp-serial throughput path (kind 8): alpha checkpoints forward, chunked beta + gradients backward.
 template <int CPL, int L>
 void launch_ws(const WsParams& p, cudaStream_t stream) {
     const FbArgs& a = p.a;
-    const size_t fwd_smem = 128 + (size_t)p.NS * 2 * p.R * a.max_u * sizeof(float);
-    const size_t bwd_smem = 128 + (size_t)kWsBwdStages * 2 * L * a.max_u * sizeof(float);
+    size_t fwd_smem = 128 + (size_t)p.NS * 2 * p.R * a.max_u * sizeof(float);
+    size_t bwd_smem = 128 + (size_t)kWsBwdStages * 2 * L * a.max_u * sizeof(float);
+    // Even waves: all utterances of a wave finish together, so B = 2048 at 13 resident warps per SM is one full wave
+    // plus a sliver (124 utterances on an otherwise idle GPU).  Asking for more shared memory than needed caps the
+    // resident warps per SM at a count that divides the batch into equal waves (ws_resident_cap).
+    {
+        const size_t sm_bytes = 228 * 1024, per_cta = 1024;  // shared memory per SM, reserved per resident CTA
+        static const int env_cap = [] { const char* e = std::getenv("SSNT_WS_RESIDENT"); return e ? std::atoi(e) : -1; }();  // tuning aid: 0 off, n forces
+        const int fit_f = (int)(sm_bytes / (fwd_smem + per_cta)), fit_b = (int)(sm_bytes / (bwd_smem + per_cta));
+        const int cap_f = env_cap > 0 ? env_cap : (env_cap == 0 ? fit_f : ws_resident_cap((size_t)a.batch_size, sm_count(), fit_f));
+        const int cap_b = env_cap > 0 ? env_cap : (env_cap == 0 ? fit_b : ws_resident_cap((size_t)a.batch_size, sm_count(), fit_b));
+        if (cap_f >= 3 && cap_f < fit_f) fwd_smem = std::min<size_t>(sm_bytes / cap_f - per_cta - 256, 100 * 1024);
+        if (cap_b >= 3 && cap_b < fit_b) bwd_smem = std::min<size_t>(sm_bytes / cap_b - per_cta - 256, 100 * 1024);
+    }
     static bool configured_[64] = {};  // per device
     bool& configured = configured_[device_ordinal()];
     if (!configured) {
