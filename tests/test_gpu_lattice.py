@@ -345,6 +345,18 @@ def test_split_kernel_infeasible_and_masked(product, oracle_mod):
 
 
 @pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,T,U", [(2048, 40, 128), (2500, 24, 256)])
+def test_warp_serial_even_waves(product, oracle_mod, B, T, U):
+    """Batch sizes at which the warp-serial kernels cap their resident warps per SM (one full wave plus a sliver
+    otherwise; csrc/fb_kernels.cu::ws_resident_cap): auto-dispatch takes kind 8, results against the fp64 oracle."""
+    le, ls = make_inputs(B, T, U, seed=B + T)
+    t_len, u_len = ragged_lengths(B, T, U, seed=B)
+    want = oracle_mod.forward_backward(le, ls, t_len, u_len)
+    got, used = _run(product, le, ls, t_len, u_len, "device")
+    assert used == 8
+    _check(got, want, t_len, u_len)
+
+
 def test_auto_dispatch_small_and_large_batches(product):
     """Every aligned shape up to max_u = 256 takes the time-parallel kernels (kind 6), whatever the batch size."""
     import torch
