@@ -431,7 +431,8 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.gridDim = dim3(tasks);
         cfg.blockDim = dim3(32);
         cfg.dynamicSmemBytes = chunk_smem;
-        if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, true>, pg));
+        if (lg && full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, true, true>, pg));
+        else if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, true>, pg));
         else if (full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, false, true>, pg));
         else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_build_kernel<CPL, L, false>, pg));
     }
@@ -449,7 +450,8 @@ void launch_tp(const TpParams& p, cudaStream_t stream) {
         cfg.gridDim = dim3(tasks);
         cfg.blockDim = dim3(32);
         cfg.dynamicSmemBytes = chunk_smem;
-        if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, true>, pg));
+        if (lg && full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, true, true>, pg));
+        else if (lg) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, true>, pg));
         else if (full) SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, false, true>, pg));
         else SSNT_CUDA(cudaLaunchKernelEx(&cfg, tp_fill_kernel<CPL, L, false>, pg));
     }
