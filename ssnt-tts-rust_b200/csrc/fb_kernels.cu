@@ -697,7 +697,8 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     // B=512 135/137, 1024 137/212, 4096 140/232; T=800 U=128: B=1024 157/191, 4096 163/224.
     if (tls_force_kind < 0 && kind == 6 && !a.logits) {
         const size_t per_sm = (size_t)a.batch_size / (size_t)sm_count();
-        if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6)) kind = 8;
+        if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6) ||
+            (a.max_u <= 64 && per_sm >= 10)) kind = 8;  // U=64 T=800: B=888 0.37 (kind 6) vs 0.34, B=2048 0.39 vs 0.46 (kind 8)
     }
     if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
         if (kind != 1 && kind != 6 && kind != 7 && kind != 10) kind = bf_ok ? 6 : 1;
@@ -733,7 +734,10 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         p.force_fallback = kind == 7 ? 1 : 0;  // kind 7: run the time-parallel kernels but force the log-domain re-run
         // 32-token exponent groups only while the sweeps are short (<= 50 steps: no re-run in 4800 random utterances at
         // T = 800; the per-step cost is ~10 % lower than with 16-token groups)
-        const bool wide_groups = a.max_t <= 50 * kTpL;
+        // — and only while the lattice is not much longer than wide: with T / U beyond ~6 the fronts get so steep that
+        // 32-token groups lose the sweeps' agreement (B=32 U=64 T=800, random inputs: every utterance was re-run in the
+        // log domain, 265 us per step; with 16-token groups none, 33 us; U=96 T=800 likewise)
+        const bool wide_groups = a.max_t <= 50 * kTpL && 4 * (long long)a.max_t <= 25 * (long long)a.max_u;
         if (tl.CPL == 2) { if (wide_groups) launch_tp<2>(p, stream); else launch_tp<2, kTpL, 16>(p, stream); }
         else if (tl.CPL == 4) { if (wide_groups) launch_tp<4>(p, stream); else launch_tp<4, kTpL, 16>(p, stream); }
         else if (short_chunks) launch_tp<8, kTpLShort>(p, stream);

@@ -599,3 +599,15 @@ def test_short_chunk_time_parallel_kernels(product, oracle_mod, B, T, U):
         got, used = _run(product, le, ls, t_len, u_len, "device")
         assert used == 6 and product.fb_fallback_count() == fb0
         _check(got, want, t_len, u_len)
+
+
+@pytest.mark.parametrize("B,T,U", [(8, 800, 64), (8, 800, 96), (6, 600, 64), (4, 500, 48)])
+def test_long_narrow_lattices_stay_on_the_time_parallel_kernels(product, oracle_mod, B, T, U):
+    """T / U well beyond 6 with unbiased random rows (steep fronts): the boundary vectors take 16-token exponent groups
+    there, and no utterance may need the log-domain re-run (with 32-token groups every one did at U=64 T=800)."""
+    le, ls = make_inputs(B, T, U, seed=T + U)
+    want = oracle_mod.forward_backward(le, ls)
+    fb0 = product.fb_fallback_count()
+    got, used = _run(product, le, ls, None, None, "device")
+    assert used == 6 and product.fb_fallback_count() == fb0
+    _check(got, want)
