@@ -699,6 +699,11 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
         const size_t per_sm = (size_t)a.batch_size / (size_t)sm_count();
         if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6) ||
             (a.max_u <= 64 && per_sm >= 10)) kind = 8;  // U=64 T=800: B=888 0.37 (kind 6) vs 0.34, B=2048 0.39 vs 0.46 (kind 8)
+        // Very narrow (half the lanes of the time-parallel kernels idle) or very long lattices (T/U >= 20: with unbiased
+        // rows the fronts are so steep that the chunk scheme re-runs utterances in the log domain; the warp-serial
+        // kernels re-derive their frames every four rows and never did): B=1024 U=32 T=800 581 -> 337 us,
+        // B=1024 U=32 T=1600 2050 -> 662 us, B=1024 U=64 T=1600 1122 -> 659 us.
+        if ((a.max_u <= 32 && per_sm >= 6) || ((long long)a.max_t >= 20ll * a.max_u && per_sm >= 4)) kind = 8;
     }
     if (a.logits) {  // the raw-logit mode lives in the time-parallel kernels and in the log-domain warp kernel
         if (kind != 1 && kind != 6 && kind != 7 && kind != 10) kind = bf_ok ? 6 : 1;
