@@ -697,7 +697,7 @@ void launch_forward_backward(const FbArgs& a_in, cudaStream_t stream) {
     // B=512 135/137, 1024 137/212, 4096 140/232; T=800 U=128: B=1024 157/191, 4096 163/224.
     if (tls_force_kind < 0 && kind == 6 && !a.logits) {
         const size_t per_sm = (size_t)a.batch_size / (size_t)sm_count();
-        if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 6) ||
+        if ((a.max_u > 128 && per_sm >= 4) || (a.max_u > 64 && a.max_u <= 128 && per_sm >= 5) ||
             (a.max_u <= 64 && per_sm >= 10)) kind = 8;  // U=64 T=800: B=888 0.37 (kind 6) vs 0.34, B=2048 0.39 vs 0.46 (kind 8)
         // Very narrow (half the lanes of the time-parallel kernels idle) or very long lattices (T/U >= 20: with unbiased
         // rows the fronts are so steep that the chunk scheme re-runs utterances in the log domain; the warp-serial
